@@ -1,0 +1,191 @@
+"""Torch-tensor facing wrappers over the C ABI: pointer / stream / workspace plumbing only.
+
+Every function here launches the hand-written sm_100a kernels through ``_abi.lib``; nothing in this
+module computes with PyTorch ops, and there is no CPU path (CPU tensors raise).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _abi
+from ._abi import check, lib
+
+_DT = {torch.float32: _abi.ECF_F32, torch.float16: _abi.ECF_F16, torch.bfloat16: _abi.ECF_BF16}
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"ecoflap_b200 supports fp32/fp16/bf16 tensors, got {t.dtype}") from None
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("ecoflap_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+class _Workspaces:
+    """One growing scratch buffer per (device, stream): calls on one stream are serialised, so a single
+    buffer can be shared by all ops issued on it."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, device, nbytes: int) -> torch.Tensor:
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.zeros(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+            self._bufs[key] = buf
+        return buf
+
+
+_ws = _Workspaces()
+
+
+def _as_2d(x: torch.Tensor):
+    """[..., C] -> (base tensor, T, C, ld) without copying when the rows are unit-stride."""
+    C = x.shape[-1]
+    x2 = x.reshape(-1, C)
+    if x2.stride(1) != 1 or (x2.shape[0] > 1 and x2.stride(0) < C):
+        x2 = x2.contiguous()
+    ld = x2.stride(0) if x2.shape[0] > 1 else C
+    return x2, x2.shape[0], C, ld
+
+
+def sqnorm_accum(x: torch.Tensor, scaler_row: torch.Tensor, rescale: float, inv_n: float) -> None:
+    """scaler_row = scaler_row * rescale + colsum(x^2) * inv_n   (A1, wanda_pruner.py:71-84)."""
+    _require_cuda(x, scaler_row)
+    assert scaler_row.dtype == torch.float32 and scaler_row.is_contiguous()
+    x2, T, C, ld = _as_2d(x)
+    assert scaler_row.numel() == C
+    need = lib.ecf_workspace_bytes(_abi.OP_SQNORM, T, C)
+    ws = _ws.get(x.device, need)
+    check(lib.ecf_sqnorm_accum(x2.data_ptr(), dtype_code(x2), T, C, ld, scaler_row.data_ptr(), float(rescale),
+                               float(inv_n), ws.data_ptr(), ws.numel(), _stream(x)))
+
+
+def _weight_2d(W: torch.Tensor):
+    assert W.dim() == 2 and W.stride(1) == 1, "weight must be a row-major 2-D tensor"
+    return W.shape[0], W.shape[1], (W.stride(0) if W.shape[0] > 1 else W.shape[1])
+
+
+def alloc_mask_bits(R: int, C: int, device) -> torch.Tensor:
+    return torch.zeros((R, (C + 7) // 8), dtype=torch.uint8, device=device)
+
+
+def unpack_mask_bits(mask_bits: torch.Tensor, C: int) -> torch.Tensor:
+    """Packed mask -> bool [R, C] (test/debug helper; bit j of byte v is column 8v+j)."""
+    shifts = torch.arange(8, device=mask_bits.device, dtype=torch.uint8)
+    bits = (mask_bits.unsqueeze(-1) >> shifts) & 1
+    return bits.reshape(mask_bits.shape[0], -1)[:, :C].bool()
+
+
+def wanda_row_select_apply(W, scaler_row, k_per_row: int, mask_bits=None, n_zero=None) -> None:
+    """Zero, in place, the k smallest |W|*sqrt(scaler_row) of every row (A3+A4+A7)."""
+    _require_cuda(W, scaler_row, mask_bits, n_zero)
+    R, C, ld = _weight_2d(W)
+    assert scaler_row.dtype == torch.float32 and scaler_row.numel() == C and scaler_row.is_contiguous()
+    check(lib.ecf_wanda_row_select_apply(
+        W.data_ptr(), dtype_code(W), R, C, ld, scaler_row.data_ptr(), int(k_per_row),
+        mask_bits.data_ptr() if mask_bits is not None else None,
+        mask_bits.stride(0) if mask_bits is not None else 0,
+        n_zero.data_ptr() if n_zero is not None else None, None, 0, _stream(W)))
+
+
+def wanda_layer_thresh_apply(W, scaler_row, kth_index: int, thres_out=None, mask_bits=None, n_zero=None) -> None:
+    """Zero, in place, every entry whose score is <= the kth_index-th smallest score (A3+A5+A7)."""
+    _require_cuda(W, scaler_row, mask_bits, n_zero, thres_out)
+    R, C, ld = _weight_2d(W)
+    assert scaler_row.dtype == torch.float32 and scaler_row.numel() == C and scaler_row.is_contiguous()
+    if not (0 <= kth_index < R * C):
+        raise IndexError(f"index {kth_index} is out of bounds for dimension 0 with size {R * C}")
+    need = lib.ecf_workspace_bytes(_abi.OP_LAYER_THRESH, R, C)
+    ws = _ws.get(W.device, need)
+    check(lib.ecf_wanda_layer_thresh_apply(
+        W.data_ptr(), dtype_code(W), R, C, ld, scaler_row.data_ptr(), int(kth_index),
+        thres_out.data_ptr() if thres_out is not None else None,
+        mask_bits.data_ptr() if mask_bits is not None else None,
+        mask_bits.stride(0) if mask_bits is not None else 0,
+        n_zero.data_ptr() if n_zero is not None else None, ws.data_ptr(), ws.numel(), _stream(W)))
+
+
+def zo_perturb(W: torch.Tensor, z: torch.Tensor, scaling: float, eps: float) -> None:
+    """W = rn(W + rn(rn(scaling*z)*eps)) in W's dtype, in place (A11)."""
+    _require_cuda(W, z)
+    assert W.is_contiguous() and z.is_contiguous() and W.dtype == z.dtype and W.numel() == z.numel()
+    check(lib.ecf_zo_perturb(W.data_ptr(), dtype_code(W), W.numel(), z.data_ptr(), float(scaling), float(eps),
+                             _stream(W)))
+
+
+def count_zero(W: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """out(uint64 as int64 tensor) += number of zeros in W (A17)."""
+    _require_cuda(W)
+    Wc = W if W.is_contiguous() else W.contiguous()
+    if out is None:
+        out = torch.zeros(1, dtype=torch.int64, device=W.device)
+    check(lib.ecf_count_zero(Wc.data_ptr(), dtype_code(Wc), Wc.numel(), out.data_ptr(), _stream(W)))
+    return out
+
+
+def group_abs_reduce(tensors):
+    """Per tensor: (sum|w|, sum w^2) as two float64 CUDA tensors, one launch for the whole list (A14)."""
+    tensors = [t if t.is_contiguous() else t.contiguous() for t in tensors]
+    _require_cuda(*tensors)
+    dev = tensors[0].device
+    chunk = lib.ecf_group_reduce_chunk_elems()
+    n = len(tensors)
+    table = (_abi.TensorDesc * n)()
+    cb = 0
+    for i, t in enumerate(tensors):
+        table[i].ptr = t.data_ptr()
+        table[i].numel = t.numel()
+        table[i].dtype = dtype_code(t)
+        table[i].reserved = 0
+        table[i].chunk_begin = cb
+        cb += max(1, (t.numel() + chunk - 1) // chunk)
+    raw = bytes(table)
+    host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+    d_table = host.to(dev, non_blocking=False)
+    sum_abs = torch.zeros(n, dtype=torch.float64, device=dev)
+    sum_sq = torch.zeros(n, dtype=torch.float64, device=dev)
+    need = lib.ecf_workspace_bytes(_abi.OP_GROUP_REDUCE, n, cb)
+    ws = _ws.get(dev, need)
+    check(lib.ecf_group_abs_reduce(d_table.data_ptr(), n, cb, sum_abs.data_ptr(), sum_sq.data_ptr(), ws.data_ptr(),
+                                   ws.numel(), _stream(tensors[0])))
+    return sum_abs, sum_sq
+
+
+def hessian_accum(x: torch.Tensor, H: torch.Tensor, alpha: float, beta: float) -> None:
+    """H = beta*H + alpha * x^T x  on tcgen05 tensor cores (A8, sparsegpt_pruner.py:71-82)."""
+    _require_cuda(x, H)
+    assert H.dtype == torch.float32 and H.dim() == 2 and H.stride(1) == 1
+    x2, T, C, ld = _as_2d(x)
+    assert H.shape[0] == C and H.shape[1] == C
+    need = lib.ecf_workspace_bytes(_abi.OP_HESSIAN, T, C)
+    ws = _ws.get(x.device, need)
+    check(lib.ecf_hessian_accum(x2.data_ptr(), dtype_code(x2), T, C, ld, H.data_ptr(), H.stride(0), float(alpha),
+                                float(beta), ws.data_ptr(), ws.numel(), _stream(x)))
+
+
+def obs_prune(W: torch.Tensor, Hinv: torch.Tensor, kth_per_block, blocksize: int = 128) -> None:
+    """SparseGPT block loop on an fp32 working copy W, in place (A10, sparsegpt_pruner.py:172-213)."""
+    _require_cuda(W, Hinv)
+    assert W.dtype == torch.float32 and Hinv.dtype == torch.float32
+    R, C, ldw = _weight_2d(W)
+    assert Hinv.shape == (C, C) and Hinv.stride(1) == 1
+    nb = (C + blocksize - 1) // blocksize
+    assert len(kth_per_block) == nb
+    arr = (ctypes.c_int64 * nb)(*[int(v) for v in kth_per_block])
+    need = lib.ecf_workspace_bytes(_abi.OP_OBS, R, C)
+    ws = _ws.get(W.device, need)
+    check(lib.ecf_obs_prune(W.data_ptr(), R, C, ldw, Hinv.data_ptr(), Hinv.stride(0), arr, int(blocksize),
+                            ws.data_ptr(), ws.numel(), _stream(W)))

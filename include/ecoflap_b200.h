@@ -1,0 +1,153 @@
+/*
+ * ecoflap_b200 -- C ABI of the B200 (sm_100a) implementation of ECoFLaP's pruning hot path.
+ *
+ * The reference (ylsung/ECoFLaP) is pure Python/PyTorch and has no FFI boundary of its own; each
+ * entry point below replaces one ATen call sequence inside the reference's pruner classes (cited
+ * per function, paths relative to the reference root).  A maintainer binds these with ctypes --
+ * see INTEGRATION.md for the stubs that replace the bodies of WrappedGPT.add_batch,
+ * SparseGPT.add_batch/fasterprune, the score/sort/mask block of *_prune() and
+ * LayerSparsity.zo_perturb_parameters.
+ *
+ * Conventions
+ *   - every pointer is a BORROWED DEVICE pointer (e.g. torch tensor.data_ptr()); the library never
+ *     allocates or frees caller memory.  Scratch comes from a caller-supplied workspace whose size
+ *     is returned by ecf_workspace_bytes().
+ *   - every call is asynchronous on the supplied CUDA stream and re-entrant across streams
+ *     (one workspace per stream).  The only global state is the thread-local error string.
+ *   - return value: 0 = OK, negative = error (text through ecf_last_error()).
+ *   - dtype enum: 0 = fp32, 1 = fp16, 2 = bf16.  Sizes are int64_t.  Matrices are row-major with a
+ *     leading dimension `ld` counted in ELEMENTS.
+ *   - k / kth_index are computed ON THE HOST with the reference's exact Python expression
+ *     (int(C * s), int(numel * s)); the kernels never see a sparsity ratio.
+ *   - there is NO CPU fallback: on a machine without an sm_100 device every compute entry point
+ *     returns ECF_ERR_NO_DEVICE.
+ */
+#ifndef ECOFLAP_B200_H_
+#define ECOFLAP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECF_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define ECF_API __attribute__((visibility("default")))
+#else
+#define ECF_API
+#endif
+
+typedef struct CUstream_st* ecf_stream_t; /* == cudaStream_t */
+
+enum ecf_dtype { ECF_F32 = 0, ECF_F16 = 1, ECF_BF16 = 2 };
+
+enum ecf_status {
+  ECF_OK = 0,
+  ECF_ERR_INVALID = -1,   /* bad argument (null pointer, negative size, unsupported shape)   */
+  ECF_ERR_WORKSPACE = -2, /* workspace too small                                              */
+  ECF_ERR_CUDA = -3,      /* a CUDA runtime call failed                                       */
+  ECF_ERR_NO_DEVICE = -4, /* no sm_100 device                                                 */
+  ECF_ERR_RANGE = -5      /* kth_index >= numel (the reference raises IndexError here)        */
+};
+
+enum ecf_op {
+  ECF_OP_SQNORM = 0,
+  ECF_OP_ROW_SELECT = 1,
+  ECF_OP_LAYER_THRESH = 2,
+  ECF_OP_GROUP_REDUCE = 3,
+  ECF_OP_HESSIAN = 4,
+  ECF_OP_OBS = 5
+};
+
+ECF_API int ecf_version(void);
+ECF_API const char* ecf_last_error(void);
+/* number of SMs of the current device, or a negative ecf_status */
+ECF_API int ecf_device_sm_count(void);
+
+/* Scratch bytes needed by `op` for an R x C problem (T x C for SQNORM/HESSIAN; for GROUP_REDUCE
+ * R = number of tensors and C = total number of chunks, see ecf_group_reduce_chunk_elems). */
+ECF_API size_t ecf_workspace_bytes(int op, int64_t R, int64_t C);
+
+/* A1 -- WrappedGPT.add_batch, LAVIS/lavis/compression/pruners/wanda_pruner.py:71-84
+ * (CoOp/trainers/pruners/wanda_pruner.py:159-172, UPop/pruners/wanda_pruner.py:65-78).
+ *   scaler_row[c] = scaler_row[c] * rescale + (sum_t x[t,c]^2) * inv_n
+ * x is the hook input flattened to [T, C]; the host passes rescale = n/(n+B), inv_n = 1/(n+B).
+ * fp32 accumulation, deterministic summation order. */
+ECF_API int ecf_sqnorm_accum(const void* x, int x_dtype, int64_t T, int64_t C, int64_t ld,
+                     float* scaler_row, float rescale, float inv_n,
+                     void* ws, size_t ws_bytes, ecf_stream_t stream);
+
+/* A3+A4+A7 -- per-ROW Wanda select, wanda_pruner.py:260,272-279 (T5); CoOp wanda_pruner.py:357,
+ * 379-383 (CLIP); UPop wanda_pruner.py:243,253-260 (BERT); LLaMA/image_classifiers/prune_utils.py:35-38.
+ * For every row: score = fp32(|w|) * sqrtf(scaler_row[c]); the k_per_row smallest scores (ties ->
+ * lower column index, i.e. torch.sort(stable=True)[:, :k]) are zeroed IN PLACE.
+ *   mask_bits (nullable): packed mask, bit (c & 7) of byte mask_bits[r * mask_ld + (c >> 3)] = pruned
+ *   n_zero    (nullable): += number of zero-valued weights after the call (check_sparsity, :139-163) */
+ECF_API int ecf_wanda_row_select_apply(void* W, int w_dtype, int64_t R, int64_t C, int64_t ld,
+                               const float* scaler_row, int64_t k_per_row,
+                               uint8_t* mask_bits, int64_t mask_ld, unsigned long long* n_zero,
+                               void* ws, size_t ws_bytes, ecf_stream_t stream);
+
+/* A3+A5+A7 -- per-LAYER threshold select, wanda_pruner.py:541,553-558 (ViT); UPop :502,512-517;
+ * prune_utils.py:28-31.  thres = kth_index-th (0-based) smallest score of the whole matrix; every
+ * entry with score <= thres is zeroed in place (>= kth_index+1 entries, more on ties).
+ *   thres_out (nullable): device float receiving thres. */
+ECF_API int ecf_wanda_layer_thresh_apply(void* W, int w_dtype, int64_t R, int64_t C, int64_t ld,
+                                 const float* scaler_row, int64_t kth_index, float* thres_out,
+                                 uint8_t* mask_bits, int64_t mask_ld, unsigned long long* n_zero,
+                                 void* ws, size_t ws_bytes, ecf_stream_t stream);
+
+/* A14 -- group aggregation, layer_single_base_pruner.py:361-377 together with the |W| / W^2 factors
+ * of :467,:556-559.  One launch over a DEVICE table of tensors; per tensor i:
+ *   sum_abs[i] = sum |w|,  sum_sq[i] = sum w^2      (fp32 partials, fp64 final combine)
+ * The host multiplies by g-hat and adds per group.  chunk_begin is the running count of
+ * ecf_group_reduce_chunk_elems()-sized chunks before tensor i (table[n-1] end = total_chunks). */
+typedef struct ecf_tensor_desc {
+  const void* ptr;
+  int64_t numel;
+  int32_t dtype;
+  int32_t reserved;
+  int64_t chunk_begin;
+} ecf_tensor_desc;
+ECF_API int64_t ecf_group_reduce_chunk_elems(void);
+ECF_API int ecf_group_abs_reduce(const ecf_tensor_desc* d_table, int n_tensors, int64_t total_chunks,
+                         double* sum_abs, double* sum_sq,
+                         void* ws, size_t ws_bytes, ecf_stream_t stream);
+
+/* A11 -- LayerSparsity.zo_perturb_parameters, layer_single_base_pruner.py:473-486.
+ *   w = rn(w + rn(rn(scaling * z) * eps)), each rounding in the parameter dtype (torch evaluates
+ * `scaling_factor * z * zo_eps` left to right in w's dtype).  z is drawn by the caller with
+ * torch.normal after torch.manual_seed so the RNG stream is the reference's own. */
+ECF_API int ecf_zo_perturb(void* W, int w_dtype, int64_t numel, const void* z,
+                   double scaling, double eps, ecf_stream_t stream);
+
+/* A17 -- (W == 0).sum(), wanda_pruner.py:154; evaluate_blip.py:432-436.  *n_zero += count. */
+ECF_API int ecf_count_zero(const void* W, int w_dtype, int64_t numel, unsigned long long* n_zero,
+                   ecf_stream_t stream);
+
+/* A8 -- SparseGPT.add_batch, sparsegpt_pruner.py:71-82 (CoOp sparsegpt_pruner.py:160-171).
+ *   H = beta * H + alpha * X^T X          X: [T, C] row-major, H: [C, C] fp32 row-major (ldh)
+ * tcgen05 tensor cores, fp32 accumulation in TMEM.  fp16/bf16 products are exact; fp32 inputs are
+ * split into bf16 hi/mid terms inside the workspace (error ~2^-16).  The host passes
+ * beta = n/(n+B), alpha = 2/(n+B). */
+ECF_API int ecf_hessian_accum(const void* x, int x_dtype, int64_t T, int64_t C, int64_t ld,
+                      float* H, int64_t ldh, float alpha, float beta,
+                      void* ws, size_t ws_bytes, ecf_stream_t stream);
+
+/* A10 -- SparseGPT.fasterprune block loop, sparsegpt_pruner.py:172-213 (prune_n == 0).
+ * W: [R, C] fp32 working copy (dead columns already zeroed), Hinv: [C, C] fp32 upper Cholesky
+ * factor from the prologue (:96-163, cuSOLVER through torch.linalg).  For each `blocksize`-column
+ * block: per-tile threshold at index kth_per_block[b] (= int(R*count*s), host-computed), the
+ * in-block sequential OBS sweep, then the trailing update W[:, i2:] -= Err @ Hinv[i1:i2, i2:]. */
+ECF_API int ecf_obs_prune(float* W, int64_t R, int64_t C, int64_t ldw,
+                  const float* Hinv, int64_t ldh,
+                  const int64_t* kth_per_block /*host array, ceil(C/blocksize) entries*/,
+                  int blocksize, void* ws, size_t ws_bytes, ecf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECOFLAP_B200_H_ */

@@ -1,0 +1,266 @@
+"""Parity of the CUDA path (through the C ABI) with the numpy oracle and the reference-generated
+golden fixtures.  Needs a B200; every test is marked gpu."""
+import numpy as np
+import pytest
+import torch
+
+import ecoflap_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TD = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def to_dev(a, dt):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev()).to(TD[dt])
+
+
+def f32(t):
+    return t.detach().float().cpu().numpy()
+
+
+def synth_w(R, C, dt, seed, scale=0.02):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(R, C, generator=g) * scale).to(TD[dt])
+
+
+def synth_norm(C, seed, outliers=True, dead=True):
+    rng = np.random.default_rng(seed)
+    s = (rng.random(C).astype(np.float32) + 0.05) * 3.0
+    if outliers and C >= 8:
+        s[rng.integers(0, C, size=3)] *= 900.0
+    if dead and C >= 8:
+        s[int(rng.integers(0, C))] = 0.0
+    return s
+
+
+# ---------------------------------------------------------------------------- A1
+def test_sqnorm_golden():
+    from ecoflap_b200 import ops
+
+    g = np.load("tests/golden/norm_accum.npz")
+    for name in [str(c) for c in g["cases"]]:
+        dt = str(g[f"{name}__dtype"])
+        nb = int(g[f"{name}__nb"])
+        C = g[f"{name}__x0"].shape[-1]
+        s = torch.zeros(C, dtype=torch.float32, device=dev())
+        n = 0
+        for i in range(nb):
+            x = to_dev(g[f"{name}__x{i}"], dt)
+            b = 1 if x.dim() == 2 else x.shape[0]
+            ops.sqnorm_accum(x, s, n / (n + b), 1.0 / (n + b))
+            n += b
+            ref = g[f"{name}__s{i}"]
+            # north_star tolerance: norms within 1e-3 relative
+            np.testing.assert_allclose(f32(s), ref, rtol=1e-4, atol=1e-30, err_msg=f"{name} batch {i}")
+
+
+@pytest.mark.parametrize("dt", ["fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("shape", [(8, 257, 1408), (3, 64, 2048), (2, 197, 768), (1, 2048, 4096), (5, 7, 50), (1, 1, 8)])
+def test_sqnorm_vs_oracle(dt, shape):
+    from ecoflap_b200 import ops
+
+    g = torch.Generator().manual_seed(hash((dt, shape)) % 1000)
+    x = torch.randn(*shape, generator=g)
+    x[..., 1] *= 30.0
+    if shape[-1] > 4:
+        x[..., 4] = 0.0
+    x = x.to(TD[dt])
+    s = torch.rand(shape[-1], generator=g).float()
+    s_dev = s.to(dev())
+    n0, b = 24, shape[0]
+    ops.sqnorm_accum(x.to(dev()), s_dev, n0 / (n0 + b), 1.0 / (n0 + b))
+    exact = s.numpy().astype(np.float64) * (n0 / (n0 + b)) + orc.sqnorm_columns(f32(x)) / (n0 + b)
+    np.testing.assert_allclose(f32(s_dev), exact, rtol=2e-5, atol=1e-30)
+    assert f32(s_dev)[4] == pytest.approx(s.numpy()[4] * np.float32(n0 / (n0 + b)), rel=1e-6) or shape[-1] <= 4
+
+
+def test_sqnorm_noncontiguous_rows_and_determinism():
+    from ecoflap_b200 import ops
+
+    big = torch.randn(300, 1024, device=dev(), dtype=torch.float16)
+    view = big[:, 128:128 + 512]  # ld = 1024 > C = 512
+    a = torch.zeros(512, device=dev())
+    b = torch.zeros(512, device=dev())
+    ops.sqnorm_accum(view, a, 0.0, 1.0)
+    ops.sqnorm_accum(view.contiguous(), b, 0.0, 1.0)
+    assert torch.equal(a, b)  # fixed summation order -> bit identical
+    np.testing.assert_allclose(f32(a), orc.sqnorm_columns(f32(view)), rtol=2e-5)
+
+
+# ---------------------------------------------------------------------------- A3+A4+A7
+ROW_SHAPES = [(64, 2048), (48, 5120), (40, 4096), (24, 11008), (96, 768), (33, 1408), (16, 512), (7, 96), (5, 50), (4, 8)]
+
+
+@pytest.mark.parametrize("dt", ["fp16", "bf16", "fp32"])
+@pytest.mark.parametrize("shape", ROW_SHAPES)
+def test_row_select_bit_exact(dt, shape):
+    from ecoflap_b200 import ops
+
+    R, C = shape
+    if dt == "fp32" and C > 8192:
+        pytest.skip("fp32 rows longer than 8192 are outside the supported range")
+    W = synth_w(R, C, dt, seed=R * 131 + C)
+    s = synth_norm(C, seed=C)
+    for sparsity in (0.5, 0.5199999809265137, 0.3, 0.0, 1.0):
+        k = orc.row_k(C, sparsity)
+        Wd = W.clone().to(dev())
+        mb = ops.alloc_mask_bits(R, C, dev())
+        nz = torch.zeros(1, dtype=torch.int64, device=dev())
+        ops.wanda_row_select_apply(Wd, torch.from_numpy(s).to(dev()), k, mask_bits=mb, n_zero=nz)
+        Wref, mref = orc.wanda_prune_rows(f32(W), s, sparsity)
+        got = f32(Wd)
+        assert np.array_equal(got.view(np.uint32), Wref.view(np.uint32)), (dt, shape, sparsity)
+        assert np.array_equal(ops.unpack_mask_bits(mb, C).cpu().numpy(), mref)
+        assert int(nz.item()) == orc.count_zero(Wref)
+
+
+@pytest.mark.parametrize("dt", ["fp16", "bf16"])
+def test_row_select_adversarial_ties(dt):
+    """duplicated columns, all-zero norms, already-pruned weights: ties must go to the lower index."""
+    from ecoflap_b200 import ops
+
+    R, C = 32, 2048
+    W = synth_w(R, C, dt, seed=5)
+    W[:, 1024:] = W[:, :1024]  # every score appears twice
+    W[3] = 0  # a whole row of ties
+    W[4, ::2] = 0  # half the row already pruned
+    W[5] = W[5, 0]  # constant row
+    s = np.full(C, 2.0, dtype=np.float32)
+    s[100:200] = 0.0  # dead channels -> score exactly 0
+    for sparsity in (0.5, 0.25, 0.75, 0.04):
+        k = orc.row_k(C, sparsity)
+        Wd = W.clone().to(dev())
+        ops.wanda_row_select_apply(Wd, torch.from_numpy(s).to(dev()), k)
+        Wref, _ = orc.wanda_prune_rows(f32(W), s, sparsity)
+        assert np.array_equal(f32(Wd).view(np.uint32), Wref.view(np.uint32)), sparsity
+    s0 = np.zeros(C, dtype=np.float32)  # all-zero norms: prune the first k columns of every row
+    Wd = W.clone().to(dev())
+    ops.wanda_row_select_apply(Wd, torch.from_numpy(s0).to(dev()), 1000)
+    Wref, _ = orc.wanda_prune_rows(f32(W), s0, 1000 / C)
+    assert np.array_equal(f32(Wd).view(np.uint32), Wref.view(np.uint32))
+
+
+def test_row_select_strided_weight():
+    from ecoflap_b200 import ops
+
+    big = synth_w(16, 4096, "bf16", seed=9).to(dev())
+    view = big[:, 1024:3072]
+    s = synth_norm(2048, seed=3)
+    ref, _ = orc.wanda_prune_rows(f32(view), s, 0.5)
+    before = big.clone()
+    ops.wanda_row_select_apply(view, torch.from_numpy(s).to(dev()), 1024)
+    assert np.array_equal(f32(view), ref)
+    assert torch.equal(big[:, :1024], before[:, :1024]) and torch.equal(big[:, 3072:], before[:, 3072:])
+
+
+# ---------------------------------------------------------------------------- A3+A5+A7
+LAYER_SHAPES = [(2304, 768), (768, 3072), (4224, 1408), (100, 50), (7, 96), (3, 8)]
+
+
+@pytest.mark.parametrize("dt", ["fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("shape", LAYER_SHAPES)
+def test_layer_thresh_bit_exact(dt, shape):
+    from ecoflap_b200 import ops
+
+    R, C = shape
+    W = synth_w(R, C, dt, seed=R + 7 * C)
+    s = synth_norm(C, seed=C + 1)
+    for sparsity in (0.5, 0.41999998688697815, 0.0):
+        idx = orc.layer_kth_index(R * C, sparsity)
+        Wd = W.clone().to(dev())
+        th = torch.zeros(1, device=dev())
+        mb = ops.alloc_mask_bits(R, C, dev())
+        nz = torch.zeros(1, dtype=torch.int64, device=dev())
+        ops.wanda_layer_thresh_apply(Wd, torch.from_numpy(s).to(dev()), idx, thres_out=th, mask_bits=mb, n_zero=nz)
+        Wref, mref, thres = orc.wanda_prune_layer(f32(W), s, sparsity)
+        assert float(th.item()) == float(thres)
+        assert np.array_equal(f32(Wd).view(np.uint32), Wref.view(np.uint32)), (dt, shape, sparsity)
+        assert np.array_equal(ops.unpack_mask_bits(mb, C).cpu().numpy(), mref)
+        assert int(nz.item()) == orc.count_zero(Wref)
+
+
+def test_layer_thresh_ties_and_range():
+    from ecoflap_b200 import ops
+
+    W = synth_w(64, 256, "fp16", seed=2)
+    W[:, 128:] = W[:, :128]
+    s = np.ones(256, dtype=np.float32)
+    Wd = W.clone().to(dev())
+    ops.wanda_layer_thresh_apply(Wd, torch.from_numpy(s).to(dev()), 64 * 256 // 2)
+    Wref, mref, _ = orc.wanda_prune_layer(f32(W), s, 0.5)
+    assert np.array_equal(f32(Wd), Wref)
+    assert mref.sum() >= 64 * 256 // 2 + 1  # the '<=' rule prunes idx+1 entries plus ties
+    with pytest.raises(IndexError):  # sparsity 1.0 -> index == numel, the reference raises IndexError
+        ops.wanda_layer_thresh_apply(Wd, torch.from_numpy(s).to(dev()), 64 * 256)
+
+
+# ---------------------------------------------------------------------------- A11
+def test_zo_perturb_golden_bit_exact():
+    from ecoflap_b200 import ops
+
+    g = np.load("tests/golden/zo_perturb.npz")
+    eps = float(g["eps"])
+    for dt in [str(c) for c in g["cases"]]:
+        w = to_dev(g[f"{dt}__W0"], dt)
+        z = to_dev(g[f"{dt}__z"], dt)
+        for step, sc in enumerate((1, -2, 1)):
+            ops.zo_perturb(w, z, sc, eps)
+            ref = g[f"{dt}__W{step + 1}"]
+            assert np.array_equal(f32(w).view(np.uint32), ref.view(np.uint32)), (dt, step)
+
+
+@pytest.mark.parametrize("dt", ["fp32", "fp16", "bf16"])
+def test_zo_perturb_large_vs_oracle(dt):
+    from ecoflap_b200 import ops
+
+    g = torch.Generator().manual_seed(4)
+    w = (torch.randn(1037, 2051, generator=g) * 0.02).to(TD[dt])
+    z = torch.randn(1037, 2051, generator=g).to(TD[dt])
+    wd = w.clone().to(dev())
+    ops.zo_perturb(wd, z.to(dev()), -2, 1e-3)
+    ref = orc.zo_perturb(f32(w), f32(z), -2, 1e-3, dt)
+    assert np.array_equal(f32(wd).view(np.uint32), ref.view(np.uint32))
+
+
+# ---------------------------------------------------------------------------- A14 / A17
+def test_group_abs_reduce_vs_oracle():
+    from ecoflap_b200 import ops
+
+    g = torch.Generator().manual_seed(6)
+    shapes = [(2048, 2048, "bf16"), (5120, 2048, "bf16"), (4224, 1408, "fp16"), (768, 3072, "fp32"), (7, 13, "fp16"),
+              (1, 1, "fp32"), (333, 1001, "bf16")]
+    ts = [(torch.randn(r, c, generator=g) * 0.02).to(TD[dt]) for r, c, dt in shapes]
+    sa, sq = ops.group_abs_reduce([t.to(dev()) for t in ts])
+    for i, t in enumerate(ts):
+        a, q = orc.abs_and_square_sums(f32(t))
+        assert sa[i].item() == pytest.approx(a, rel=1e-5)
+        assert sq[i].item() == pytest.approx(q, rel=1e-5)
+    sa2, sq2 = ops.group_abs_reduce([t.to(dev()) for t in ts])
+    assert torch.equal(sa, sa2) and torch.equal(sq, sq2)  # deterministic
+
+
+def test_count_zero():
+    from ecoflap_b200 import ops
+
+    for dt in ("fp32", "fp16", "bf16"):
+        w = synth_w(513, 1031, dt, seed=1)
+        w[w.abs() < 0.01] = 0
+        w[0, 0] = -0.0
+        out = ops.count_zero(w.to(dev()))
+        assert int(out.item()) == orc.count_zero(f32(w))
+
+
+# ---------------------------------------------------------------------------- error behaviour
+def test_errors_are_loud():
+    from ecoflap_b200 import _abi, ops
+
+    with pytest.raises(RuntimeError):
+        ops.sqnorm_accum(torch.zeros(4, 8), torch.zeros(8), 0.0, 1.0)  # CPU tensors: no fallback
+    W = torch.zeros(4, 70000, device=dev(), dtype=torch.float16)
+    with pytest.raises(_abi.EcfError):
+        ops.wanda_row_select_apply(W, torch.ones(70000, device=dev()), 10)
