@@ -170,7 +170,7 @@ def hessian_accum(x: torch.Tensor, H: torch.Tensor, alpha: float, beta: float) -
     assert H.dtype == torch.float32 and H.dim() == 2 and H.stride(1) == 1
     x2, T, C, ld = _as_2d(x)
     assert H.shape[0] == C and H.shape[1] == C
-    need = lib.ecf_workspace_bytes(_abi.OP_HESSIAN, T, C)
+    need = lib.ecf_workspace_bytes(_abi.OP_HESSIAN, T if x2.dtype == torch.float32 else 0, C)
     ws = _ws.get(x.device, need)
     check(lib.ecf_hessian_accum(x2.data_ptr(), dtype_code(x2), T, C, ld, H.data_ptr(), H.stride(0), float(alpha),
                                 float(beta), ws.data_ptr(), ws.numel(), _stream(x)))

@@ -264,3 +264,61 @@ def test_errors_are_loud():
     W = torch.zeros(4, 70000, device=dev(), dtype=torch.float16)
     with pytest.raises(_abi.EcfError):
         ops.wanda_row_select_apply(W, torch.ones(70000, device=dev()), 10)
+
+
+# ---------------------------------------------------------------------------- A8 (tcgen05)
+def _hess_tol(got, exact, tol=1e-3):
+    scale = np.abs(exact).max()
+    return np.abs(got - exact).max() / scale
+
+
+@pytest.mark.parametrize("dt", ["fp16", "bf16", "fp32"])
+@pytest.mark.parametrize("shape", [(3152, 768), (2056, 1408), (300, 3072), (77, 512), (4096, 2048), (64, 64), (1000, 200)])
+def test_hessian_vs_oracle(dt, shape):
+    from ecoflap_b200 import ops
+
+    T, C = shape
+    g = torch.Generator().manual_seed(T + C)
+    x = torch.randn(T, C, generator=g)
+    x[:, 1] *= 8.0
+    x[:, 5] = 0.0  # dead channel -> zero row/column
+    x = x.to(TD[dt])
+    H = torch.zeros(C, C, device=dev())
+    ops.hessian_accum(x.to(dev()), H, 2.0 / 4, 0.0)
+    exact = orc.hessian_exact([f32(x)[None]]) * (1.0 / 4)  # alpha = 2/4 instead of 2/1
+    got = f32(H)
+    # north_star tolerance: Hessians within 1e-3 relative (to max|H|)
+    assert _hess_tol(got, exact) < 2e-5, (dt, shape, _hess_tol(got, exact))
+    assert np.array_equal(got, got.T)  # mirrored exactly
+    assert np.all(got[5] == 0) and np.all(got[:, 5] == 0)
+
+
+def test_hessian_running_update_matches_reference_golden():
+    from ecoflap_b200 import ops
+
+    g = np.load("tests/golden/hessian_accum.npz")
+    for name in [str(c) for c in g["cases"]]:
+        dt = str(g[f"{name}__dtype"])
+        nb = int(g[f"{name}__nb"])
+        C = g[f"{name}__x0"].shape[-1]
+        H = torch.zeros(C, C, device=dev())
+        n = 0
+        for i in range(nb):
+            x = to_dev(g[f"{name}__x{i}"], dt)
+            b = 1 if x.dim() == 2 else x.shape[0]
+            ops.hessian_accum(x, H, 2.0 / (n + b), n / (n + b))
+            n += b
+            ref = g[f"{name}__H{i}"]
+            assert np.abs(f32(H) - ref).max() <= 1e-4 * np.abs(ref).max(), (name, i)
+
+
+def test_hessian_strided_input_and_accumulate():
+    from ecoflap_b200 import ops
+
+    big = torch.randn(500, 1024, device=dev(), dtype=torch.bfloat16)
+    view = big[:, 256:256 + 512]
+    H = torch.ones(512, 512, device=dev())
+    ops.hessian_accum(view, H, 0.5, 0.25)
+    xf = f32(view).astype(np.float64)
+    exact = 0.25 + 0.5 * xf.T @ xf
+    assert np.abs(f32(H) - exact).max() <= 2e-5 * np.abs(exact).max()
