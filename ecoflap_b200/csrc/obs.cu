@@ -1,7 +1,405 @@
-// placeholder until the OBS kernels land
+// A10 -- SparseGPT fasterprune block loop (sparsegpt_pruner.py:172-213, prune_n == 0), per 128-column block:
+//   (i)   per-TILE threshold  thresh = sort((W1^2 / diag(Hinv1)^2).flatten())[kth];  mask1 = tmp <= thresh
+//         -> 3-level radix select on the exact fp32 key (same machinery as the per-layer Wanda select)
+//   (ii)  the 128-step sequential OBS sweep -- rows are independent once mask1 is fixed, so one warp owns
+//         one row: the row block lives in 4 registers per lane, Hinv1 (128x128) in shared memory; steps
+//         whose mask bit is clear are skipped (their error is exactly zero)
+//   (iii) trailing update  W[:, i2:] -= Err1 @ Hinv[i1:i2, i2:]  on tcgen05 tensor cores: M = R, K = 128,
+//         N = C - i2; both fp32 operands are split into bf16 hi + mid terms (hi*hi + hi*mid + mid*hi,
+//         relative error ~2^-16), fp32 accumulation in TMEM, subtraction fused into the epilogue.
+//         A (= Err) is K-major, B (= Hinv rows) is MN-major; both staged by TMA with the 128-byte swizzle.
+// The reference launches ~6 tiny kernels per column (C*6 launches per layer) plus a full sort per block.
+// Bound: (i),(ii) latency/shared memory (reported separately), (iii) tensor pipe: R*C^2 flops per layer.
 #include "common.cuh"
-namespace ecf { size_t obs_workspace_bytes(int64_t, int64_t) { return 256; } }
-extern "C" int ecf_obs_prune(float*, int64_t, int64_t, int64_t, const float*, int64_t, const int64_t*, int, void*, size_t, ecf_stream_t) {
-  ecf::set_error("obs_prune: not implemented yet");
-  return ECF_ERR_INVALID;
+#include "radix_select.cuh"
+#include "umma.cuh"
+
+namespace ecf {
+
+using namespace umma;
+
+constexpr int kObsBlock = 128;  // the only block size the kernels are specialised for
+
+// ------------------------------------------------------------------ (i) tile threshold
+__device__ __forceinline__ uint32_t obs_key(float w, float d) {
+  const float s = __fdiv_rn(__fmul_rn(w, w), __fmul_rn(d, d));
+  return score_key(s);
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(256)
+    obs_hist_kernel(const float* __restrict__ W, int64_t R, int64_t ldw, const float* __restrict__ Hinv, int64_t ldh, int i1,
+                    int count, const LtState* __restrict__ state, unsigned* __restrict__ hist) {
+  __shared__ unsigned sh[2048];
+  __shared__ float dsh[kObsBlock];
+  for (int i = threadIdx.x; i < 2048; i += 256) sh[i] = 0;
+  if (threadIdx.x < kObsBlock) dsh[threadIdx.x] = threadIdx.x < count ? Hinv[(int64_t)(i1 + threadIdx.x) * ldh + i1 + threadIdx.x] : 1.f;
+  __syncthreads();
+  const uint32_t prefix = PASS == 0 ? 0u : state->prefix;
+  const int64_t total = R * count;
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+    const int64_t r = e / count;
+    const int i = (int)(e - r * count);
+    const uint32_t key = obs_key(W[r * ldw + i1 + i], dsh[i]);
+    if (PASS == 0) atomicAdd(&sh[key >> 20], 1u);
+    else if (PASS == 1) { if ((key >> 20) == prefix) atomicAdd(&sh[(key >> 10) & 1023u], 1u); }
+    else { if ((key >> 10) == prefix) atomicAdd(&sh[key & 1023u], 1u); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += 256) {
+    const unsigned c = sh[i];
+    if (c) atomicAdd(&hist[i], c);
+  }
+}
+
+// mask word (r, g) bit j  <=>  column i1 + 32 g + j is pruned
+__global__ void __launch_bounds__(256)
+    obs_mask_kernel(const float* __restrict__ W, int64_t R, int64_t ldw, const float* __restrict__ Hinv, int64_t ldh, int i1,
+                    int count, const LtState* __restrict__ state, uint32_t* __restrict__ mask /*[R][4]*/) {
+  const uint32_t tkey = state->prefix;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwords = R * 4;
+  for (int64_t wd = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); wd < nwords; wd += (int64_t)gridDim.x * 8) {
+    const int64_t r = wd >> 2;
+    const int i = (int)(wd & 3) * 32 + lane;
+    bool p = false;
+    if (i < count) {
+      const float d = Hinv[(int64_t)(i1 + i) * ldh + i1 + i];
+      p = obs_key(W[r * ldw + i1 + i], d) <= tkey;
+    }
+    const uint32_t bits = __ballot_sync(0xffffffffu, p);
+    if (lane == 0) mask[wd] = bits;
+  }
+}
+
+// ------------------------------------------------------------------ (ii) sequential sweep, one warp per row
+__global__ void __launch_bounds__(256)
+    obs_sweep_kernel(float* __restrict__ W, int64_t R, int64_t ldw, const float* __restrict__ Hinv, int64_t ldh, int i1, int count,
+                     const uint32_t* __restrict__ mask, __nv_bfloat16* __restrict__ err_hi, __nv_bfloat16* __restrict__ err_mid) {
+  extern __shared__ float hs[];  // Hinv1, [128][128], zero padded
+  for (int e = threadIdx.x; e < kObsBlock * kObsBlock; e += 256) {
+    const int i = e >> 7, j = e & 127;
+    hs[e] = (i < count && j < count) ? Hinv[(int64_t)(i1 + i) * ldh + i1 + j] : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  for (int64_t r = warp0; r < R; r += (int64_t)gridDim.x * 8) {
+    float* wrow = W + r * ldw + i1;
+    float w[4], e[4];
+    uint32_t m[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int c = s * 32 + lane;
+      w[s] = c < count ? wrow[c] : 0.f;
+      e[s] = 0.f;
+      m[s] = mask[r * 4 + s];
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      uint32_t bits = m[s];
+      while (bits) {  // warp-uniform: only pruned columns generate an error
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int i = s * 32 + b;
+        const float wi = __shfl_sync(0xffffffffu, w[s], b);
+        const float err = __fdiv_rn(wi, hs[i * kObsBlock + i]);  // (w - q) / d with q = 0
+        if (lane == b) e[s] = err;
+#pragma unroll
+        for (int s2 = 0; s2 < 4; ++s2) {
+          const int c = s2 * 32 + lane;
+          if (s2 >= s && c >= i) w[s2] = __fsub_rn(w[s2], __fmul_rn(err, hs[i * kObsBlock + c]));  // W1[:, i:] -= err (x) Hinv1[i, i:]
+        }
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int c = s * 32 + lane;
+      const bool pruned = (m[s] >> lane) & 1u;
+      if (c < count) wrow[c] = pruned ? 0.f : w[s];  // W[:, i1:i2] = Q1
+      const __nv_bfloat16 h = __float2bfloat16_rn(e[s]);
+      err_hi[r * kObsBlock + c] = h;
+      err_mid[r * kObsBlock + c] = __float2bfloat16_rn(e[s] - __bfloat162float(h));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ (iii) trailing update on tcgen05
+constexpr int kTBM = 128, kTBN = 256, kTBK = 64, kTStages = 2;
+constexpr int kTATerm = kTBM * kTBK * 2;              // 16 KB: one K-major 128 x 64 box
+constexpr int kTBBox = kTBK * 128;                    // 8 KB: one MN-major 64-column x 64-row box
+constexpr int kTBTerm = (kTBN / 64) * kTBBox;         // 32 KB
+constexpr int kTStageBytes = 2 * kTATerm + 2 * kTBTerm;  // 96 KB
+constexpr int kTSmemBytes = kTStages * kTStageBytes + 1024 + 256;
+
+struct TrailParams {
+  float* W;
+  int64_t ldw;
+  int R, i1, i2, C;
+  int MT, NT;
+  int vec_ok;
+};
+
+__global__ void __launch_bounds__(256, 1)
+    obs_trailing_kernel(const __grid_constant__ CUtensorMap ta_hi, const __grid_constant__ CUtensorMap ta_mid,
+                        const __grid_constant__ CUtensorMap tb_hi, const __grid_constant__ CUtensorMap tb_mid, TrailParams p) {
+  constexpr uint32_t kIdesc = make_idesc(kFmtBF16, kMajorK, kMajorMN, kTBM, kTBN);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kTStages * kTStageBytes);
+  uint64_t* empty_bar = full_bar + kTStages;
+  uint64_t* tmem_full = empty_bar + kTStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&ta_hi); prefetch_tmap(&ta_mid); prefetch_tmap(&tb_hi); prefetch_tmap(&tb_mid);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kTStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int total_work = p.MT * p.NT;
+  constexpr int NKB = kObsBlock / kTBK;  // 2
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int nj = w / p.MT, mi = w - nj * p.MT;
+        for (int kb = 0; kb < NKB; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], kTStageBytes);
+          uint8_t* st = smem + stage * kTStageBytes;
+          tma_load_2d(st, &ta_hi, &full_bar[stage], kb * kTBK, mi * kTBM);
+          tma_load_2d(st + kTATerm, &ta_mid, &full_bar[stage], kb * kTBK, mi * kTBM);
+          uint8_t* b = st + 2 * kTATerm;
+#pragma unroll
+          for (int j = 0; j < kTBN / 64; ++j) {
+            tma_load_2d(b + j * kTBBox, &tb_hi, &full_bar[stage], p.i2 + nj * kTBN + 64 * j, p.i1 + kb * kTBK);
+            tma_load_2d(b + kTBTerm + j * kTBBox, &tb_mid, &full_bar[stage], p.i2 + nj * kTBN + 64 * j, p.i1 + kb * kTBK);
+          }
+          if (++stage == kTStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kTBN);
+        for (int kb = 0; kb < NKB; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + stage * kTStageBytes);
+#pragma unroll
+          for (int ks = 0; ks < kTBK / 16; ++ks) {
+            // A is K-major: a K=16 step is 32 bytes inside the 128-byte swizzle atom; 8-row groups are 1024 B apart
+            const uint64_t a_hi = make_smem_desc_sw128(st + ks * 32, 16, 1024);
+            const uint64_t a_mid = make_smem_desc_sw128(st + kTATerm + ks * 32, 16, 1024);
+            const uint32_t b0 = st + 2 * kTATerm + ks * 2048;
+            const uint64_t b_hi = make_smem_desc_sw128(b0, kTBBox, 1024);
+            const uint64_t b_mid = make_smem_desc_sw128(b0 + kTBTerm, kTBBox, 1024);
+            mma_f16_ss(d_tmem, a_hi, b_hi, kIdesc, (kb | ks) != 0);
+            mma_f16_ss(d_tmem, a_hi, b_mid, kIdesc, 1);
+            mma_f16_ss(d_tmem, a_mid, b_hi, kIdesc, 1);
+          }
+          mma_commit(&empty_bar[stage]);
+          if (++stage == kTStages) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int ncols = p.C - p.i2;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int nj = w / p.MT, mi = w - nj * p.MT;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int r = mi * kTBM + q * 32 + lane;
+      float* wrow = p.W + (int64_t)r * p.ldw + p.i2;
+#pragma unroll 1
+      for (int chunk = 0; chunk < kTBN / 32; ++chunk) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTBN + chunk * 32), v);
+        tmem_ld_wait();
+        const int c0 = nj * kTBN + chunk * 32;
+        if (r < p.R) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int c = c0 + j;
+            if (c >= ncols) break;
+            if (p.vec_ok && c + 3 < ncols) {
+              float4 h = *reinterpret_cast<const float4*>(wrow + c);
+              h.x -= __uint_as_float(v[j]); h.y -= __uint_as_float(v[j + 1]); h.z -= __uint_as_float(v[j + 2]); h.w -= __uint_as_float(v[j + 3]);
+              *reinterpret_cast<float4*>(wrow + c) = h;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (c + e < ncols) wrow[c + e] -= __uint_as_float(v[j + e]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// fp32 matrix -> bf16 hi + mid (row pitch ldo)
+__global__ void __launch_bounds__(256)
+    obs_split_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ld, __nv_bfloat16* __restrict__ hi,
+                     __nv_bfloat16* __restrict__ mid, int64_t ldo) {
+  const int64_t total = rows * ldo;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ldo;
+    const int c = (int)(i - r * ldo);
+    const float v = c < cols ? x[r * ld + c] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[i] = h;
+    mid[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// ------------------------------------------------------------------ host side
+static int64_t round8(int64_t c) { return (c + 7) / 8 * 8; }
+
+struct ObsWs {
+  LtState* state;
+  unsigned* hist;
+  uint32_t* mask;
+  __nv_bfloat16 *err_hi, *err_mid, *h_hi, *h_mid;
+  size_t total;
+};
+
+static ObsWs obs_layout(void* ws, int64_t R, int64_t C) {
+  ObsWs o;
+  size_t off = 0;
+  char* b = reinterpret_cast<char*>(ws);
+  auto take = [&](size_t bytes) { char* p = b + off; off += align_up(bytes, 1024); return p; };
+  o.state = reinterpret_cast<LtState*>(take(256));
+  o.hist = reinterpret_cast<unsigned*>(take(2048 * sizeof(unsigned)));
+  o.mask = reinterpret_cast<uint32_t*>(take((size_t)R * 4 * sizeof(uint32_t)));
+  const size_t rpad = (size_t)((R + kTBM - 1) / kTBM * kTBM);
+  o.err_hi = reinterpret_cast<__nv_bfloat16*>(take(rpad * kObsBlock * 2));
+  o.err_mid = reinterpret_cast<__nv_bfloat16*>(take(rpad * kObsBlock * 2));
+  const size_t hb = (size_t)C * (size_t)round8(C) * 2;
+  o.h_hi = reinterpret_cast<__nv_bfloat16*>(take(hb));
+  o.h_mid = reinterpret_cast<__nv_bfloat16*>(take(hb));
+  o.total = off;
+  return o;
+}
+
+size_t obs_workspace_bytes(int64_t R, int64_t C) { return obs_layout(nullptr, R, C).total; }
+
+int encode_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, int dtype_code, uint64_t inner, uint64_t outer,
+                   uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+
+}  // namespace ecf
+
+extern "C" int ecf_obs_prune(float* W, int64_t R, int64_t C, int64_t ldw, const float* Hinv, int64_t ldh,
+                             const int64_t* kth_per_block, int blocksize, void* ws, size_t ws_bytes, ecf_stream_t stream_) {
+  using namespace ecf;
+  int st = check_device();
+  if (st != ECF_OK) return st;
+  ECF_REQUIRE(W != nullptr && Hinv != nullptr && kth_per_block != nullptr, ECF_ERR_INVALID, "obs_prune: null pointer");
+  ECF_REQUIRE(R > 0 && C > 0 && ldw >= C && ldh >= C, ECF_ERR_INVALID, "obs_prune: bad shape R=%lld C=%lld", (long long)R,
+              (long long)C);
+  ECF_REQUIRE(blocksize == kObsBlock, ECF_ERR_INVALID, "obs_prune: only blocksize 128 (the reference's value) is supported, got %d",
+              blocksize);
+  ECF_REQUIRE(R < (1ll << 30) && C < (1ll << 24), ECF_ERR_INVALID, "obs_prune: shape too large");
+  const size_t need = obs_workspace_bytes(R, C);
+  ECF_REQUIRE(ws != nullptr && ws_bytes >= need, ECF_ERR_WORKSPACE, "obs_prune: workspace %zu < %zu bytes", ws_bytes, need);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  ObsWs o = obs_layout(ws, R, C);
+  const int sms = sm_count();
+  const int nblocks = (int)((C + kObsBlock - 1) / kObsBlock);
+  for (int b = 0; b < nblocks; ++b) {
+    const int64_t cnt = (b + 1 < nblocks) ? kObsBlock : C - (int64_t)b * kObsBlock;
+    ECF_REQUIRE(kth_per_block[b] >= 0 && kth_per_block[b] < R * cnt, ECF_ERR_RANGE,
+                "obs_prune: kth index %lld out of range for the %lld-element tile of block %d (the reference raises IndexError)",
+                (long long)kth_per_block[b], (long long)(R * cnt), b);
+  }
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    ECF_CUDA_OK(cudaFuncSetAttribute(obs_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kObsBlock * kObsBlock * 4));
+    ECF_CUDA_OK(cudaFuncSetAttribute(obs_trailing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes));
+    attr_set = true;
+  }
+
+  // bf16 hi/mid copy of Hinv for the tensor-core trailing updates; the err buffers start zeroed
+  const int64_t ldo = round8(C);
+  const bool have_trailing = nblocks > 1;
+  CUtensorMap ta_hi, ta_mid, tb_hi, tb_mid;
+  if (have_trailing) {
+    obs_split_kernel<<<sms * 8, 256, 0, stream>>>(Hinv, C, (int)C, ldh, o.h_hi, o.h_mid, ldo);
+    ECF_CUDA_OK(cudaGetLastError());
+    const int64_t rpad = (R + kTBM - 1) / kTBM * kTBM;
+    ECF_CUDA_OK(cudaMemsetAsync(o.err_hi, 0, (size_t)rpad * kObsBlock * 2, stream));
+    ECF_CUDA_OK(cudaMemsetAsync(o.err_mid, 0, (size_t)rpad * kObsBlock * 2, stream));
+    if ((st = encode_tmap_2d(&ta_hi, o.err_hi, 2, ECF_BF16, kObsBlock, rpad, kObsBlock * 2, 64, kTBM)) != ECF_OK) return st;
+    if ((st = encode_tmap_2d(&ta_mid, o.err_mid, 2, ECF_BF16, kObsBlock, rpad, kObsBlock * 2, 64, kTBM)) != ECF_OK) return st;
+    if ((st = encode_tmap_2d(&tb_hi, o.h_hi, 2, ECF_BF16, C, C, ldo * 2, 64, kTBK)) != ECF_OK) return st;
+    if ((st = encode_tmap_2d(&tb_mid, o.h_mid, 2, ECF_BF16, C, C, ldo * 2, 64, kTBK)) != ECF_OK) return st;
+  }
+  ECF_CUDA_OK(cudaMemsetAsync(o.hist, 0, 2048 * sizeof(unsigned), stream));
+
+  for (int b = 0; b < nblocks; ++b) {
+    const int i1 = b * kObsBlock;
+    const int i2 = (int)(i1 + kObsBlock < C ? i1 + kObsBlock : C);
+    const int count = i2 - i1;
+    const int64_t elems = R * count;
+    int64_t g = (elems + 255) / 256;
+    if (g > (int64_t)sms * 8) g = (int64_t)sms * 8;
+    const unsigned grid = (unsigned)g;
+    obs_hist_kernel<0><<<grid, 256, 0, stream>>>(W, R, ldw, Hinv, ldh, i1, count, o.state, o.hist);
+    lt_scan_kernel<11, true><<<1, 1024, 0, stream>>>(o.state, o.hist, (unsigned long long)kth_per_block[b]);
+    obs_hist_kernel<1><<<grid, 256, 0, stream>>>(W, R, ldw, Hinv, ldh, i1, count, o.state, o.hist);
+    lt_scan_kernel<10, false><<<1, 1024, 0, stream>>>(o.state, o.hist, 0ull);
+    obs_hist_kernel<2><<<grid, 256, 0, stream>>>(W, R, ldw, Hinv, ldh, i1, count, o.state, o.hist);
+    lt_scan_kernel<10, false><<<1, 1024, 0, stream>>>(o.state, o.hist, 0ull);
+    int64_t gm = (R * 4 + 7) / 8;
+    if (gm > (int64_t)sms * 8) gm = (int64_t)sms * 8;
+    obs_mask_kernel<<<(unsigned)gm, 256, 0, stream>>>(W, R, ldw, Hinv, ldh, i1, count, o.state, o.mask);
+    int64_t gs = (R + 7) / 8;
+    if (gs > (int64_t)sms * 3) gs = (int64_t)sms * 3;
+    obs_sweep_kernel<<<(unsigned)gs, 256, kObsBlock * kObsBlock * 4, stream>>>(W, R, ldw, Hinv, ldh, i1, count, o.mask, o.err_hi,
+                                                                              o.err_mid);
+    if (i2 < C) {
+      TrailParams p;
+      p.W = W; p.ldw = ldw; p.R = (int)R; p.i1 = i1; p.i2 = i2; p.C = (int)C;
+      p.MT = (int)((R + kTBM - 1) / kTBM);
+      p.NT = (int)((C - i2 + kTBN - 1) / kTBN);
+      p.vec_ok = (ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+      const int total = p.MT * p.NT;
+      obs_trailing_kernel<<<total < sms ? total : sms, 256, kTSmemBytes, stream>>>(ta_hi, ta_mid, tb_hi, tb_mid, p);
+    }
+    ECF_CUDA_OK(cudaGetLastError());
+  }
+  return ECF_OK;
 }

@@ -322,3 +322,66 @@ def test_hessian_strided_input_and_accumulate():
     xf = f32(view).astype(np.float64)
     exact = 0.25 + 0.5 * xf.T @ xf
     assert np.abs(f32(H) - exact).max() <= 2e-5 * np.abs(exact).max()
+
+
+# ---------------------------------------------------------------------------- A10 (OBS sweep + tcgen05 trailing update)
+def _obs_case(R, C, s, seed, dead=False):
+    rng = np.random.default_rng(seed)
+    W = (rng.standard_normal((R, C)) * 0.02).astype(np.float32)
+    X = rng.standard_normal((2 * C, C)).astype(np.float32)
+    X[:, 1] *= 6.0
+    if dead:
+        X[:, 7] = 0.0
+    H = (2.0 / X.shape[0]) * (X.T @ X).astype(np.float32)
+    Hinv, deadcols = orc.obs_prepare_hinv(H)
+    W[:, deadcols] = 0
+    kth = [int(R * (min(i1 + 128, C) - i1) * s) for i1 in range(0, C, 128)]
+    return W, Hinv.astype(np.float32), kth
+
+
+@pytest.mark.parametrize("shape", [(64, 128), (200, 256), (96, 320), (512, 768), (130, 1000), (768, 3072)])
+def test_obs_prune_vs_oracle(shape):
+    from ecoflap_b200 import ops
+
+    R, C = shape
+    s = 0.4
+    W, Hinv, kth = _obs_case(R, C, s, seed=R + C, dead=(C == 320))
+    Wd = torch.from_numpy(W.copy()).to(dev())
+    ops.obs_prune(Wd, torch.from_numpy(Hinv).to(dev()), kth)
+    Wref, mref = orc.obs_sweep(W, Hinv, s)
+    got = f32(Wd)
+    # block 0 has identical inputs on both sides -> its mask is bit exact
+    assert np.array_equal(got[:, :128] == 0, Wref[:, :128] == 0)
+    agree = ((got == 0) == (Wref == 0)).mean()
+    assert agree >= 0.999, agree
+    # north_star: post-OBS weights within 1e-3 relative (Frobenius).  Mask decisions after block 0 depend on
+    # the fp32 rounding of earlier updates (SURVEY 'hard parts'), so the weight tolerance is checked where the
+    # two masks agree and the (rare) near-threshold flips are bounded separately.
+    same = (got == 0) == (Wref == 0)
+    rel = np.linalg.norm((got - Wref)[same]) / np.linalg.norm(Wref)
+    assert rel < 1e-3, rel
+    assert np.linalg.norm(got - Wref) / np.linalg.norm(Wref) < 5e-3
+    print(f"obs {shape}: mask agreement {agree:.6f}, rel(same-mask) {rel:.2e}")
+    # every tile obeys the '<=' rule: at least kth+1 pruned entries
+    for b, i1 in enumerate(range(0, C, 128)):
+        assert (got[:, i1:i1 + 128] == 0).sum() >= kth[b] + 1
+
+
+def test_obs_prune_reference_golden():
+    from ecoflap_b200 import ops
+
+    g = np.load("tests/golden/obs_prune.npz")
+    for name in [str(c) for c in g["cases"]]:
+        dt = str(g[f"{name}__dtype"])
+        W, H, s = g[f"{name}__W"], g[f"{name}__H"], float(g[f"{name}__s"])
+        Hinv, deadcols = orc.obs_prepare_hinv(H)
+        W = W.copy()
+        W[:, deadcols] = 0
+        R, C = W.shape
+        kth = [int(R * (min(i1 + 128, C) - i1) * s) for i1 in range(0, C, 128)]
+        Wd = torch.from_numpy(W).to(dev())
+        ops.obs_prune(Wd, torch.from_numpy(np.ascontiguousarray(Hinv)).to(dev()), kth)
+        got = orc.round_to(f32(Wd), dt)
+        ref = g[f"{name}__Wout"]
+        assert ((got == 0) == (ref == 0)).mean() >= 0.995, name
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 2e-2, name  # LAPACK (numpy vs torch) differences dominate
