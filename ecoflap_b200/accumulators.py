@@ -1,0 +1,146 @@
+"""Calibration accumulators with the reference's inner-seam interface, backed by the sm_100a kernels.
+
+``WrappedGPT``  -- LAVIS/lavis/compression/pruners/wanda_pruner.py:54-84 (CoOp wanda_pruner.py:142-172,
+                   UPop wanda_pruner.py:48-78): ``add_batch(inp, out)``, ``.scaler_row``, ``.nsamples``.
+``SparseGPT``   -- LAVIS sparsegpt_pruner.py:56-222 (CoOp sparsegpt_pruner.py:145-311):
+                   ``add_batch``, ``fasterprune(sparsity, prune_n, prune_m, blocksize, percdamp)``, ``free``.
+
+Both call the C ABI through ``ecoflap_b200.ops``; there is no PyTorch implementation behind them.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+try:  # only used for an isinstance check, exactly like the reference
+    from transformers import Conv1D as _Conv1D
+except Exception:  # pragma: no cover
+    class _Conv1D:  # type: ignore
+        pass
+
+
+def _flatten_tokens(layer, inp):
+    """[B, L, C] / [L, C] -> (batch entries B, [T, C] view).  2-D input counts as B = 1 (:72-74)."""
+    if inp.dim() == 2:
+        inp = inp.unsqueeze(0)
+    b = inp.shape[0]
+    if isinstance(layer, (nn.Linear, _Conv1D)) and inp.dim() == 3:
+        inp = inp.reshape((-1, inp.shape[-1]))
+    return b, inp
+
+
+class WrappedGPT:
+    """Running mean over samples of the per-input-channel sum of squared activations."""
+
+    def __init__(self, layer, layer_id=0, layer_name="none"):
+        self.layer = layer
+        self.dev = self.layer.weight.device
+        self.rows = layer.weight.data.shape[0]
+        self.columns = layer.weight.data.shape[1]
+        self.scaler_row = torch.zeros((self.columns), device=self.dev)
+        self.nsamples = 0
+        self.layer_id = layer_id
+        self.layer_name = layer_name
+
+    def add_batch(self, inp, out=None):
+        b, x = _flatten_tokens(self.layer, inp)
+        n = self.nsamples + b
+        # scaler_row = scaler_row * n_old/n + colsum(x^2) / n   -- one fused kernel, X read once
+        ops.sqnorm_accum(x, self.scaler_row, self.nsamples / n, 1.0 / n)
+        self.nsamples = n
+
+
+class SparseGPT:
+    """Hessian accumulator + OBS pruning.
+
+    ``H`` is kept as the running matrix the reference keeps (H*n/(n+b) + (2/n) X^T X) so that it can
+    be inspected between batches; the rescale and the product are one tcgen05 kernel call.
+    """
+
+    def __init__(self, layer):
+        self.layer = layer
+        self.dev = self.layer.weight.device
+        W = layer.weight.data
+        if isinstance(self.layer, nn.Conv2d):
+            W = W.flatten(1)
+        if isinstance(self.layer, _Conv1D):
+            W = W.t()
+        self.rows = W.shape[0]
+        self.columns = W.shape[1]
+        self.H = torch.zeros((self.columns, self.columns), device=self.dev)
+        self.nsamples = 0
+        self.max_damp_retries = 64  # the reference retries forever (sparsegpt_pruner.py:117-131)
+
+    def add_batch(self, inp, out=None):
+        b, x = _flatten_tokens(self.layer, inp)
+        n = self.nsamples + b
+        ops.hessian_accum(x, self.H, 2.0 / n, self.nsamples / n)
+        self.nsamples = n
+
+    # -- prologue helpers (cuSOLVER through torch.linalg) ---------------------------------
+    @staticmethod
+    def _repair_inf(H):
+        pos = torch.isinf(H) & (H > 0)
+        if pos.any():
+            H[pos] = torch.quantile(H, 0.999)
+        neg = torch.isinf(H) & (H < 0)
+        if neg.any():
+            H[neg] = torch.quantile(H, 0.001)
+        return H
+
+    def _cholesky_with_damping(self, H, damp, upper):
+        """cholesky; on failure (error or NaN) add damp to the diagonal and retry -- damping is applied
+        ONLY on failure, as in the reference (sparsegpt_pruner.py:117-131, 149-160)."""
+        diag = torch.arange(self.columns, device=H.device)
+        for _ in range(self.max_damp_retries):
+            L, info = torch.linalg.cholesky_ex(H, upper=upper)
+            if int(info.item()) == 0 and not torch.isnan(L).any():
+                return L
+            H[diag, diag] += damp
+        raise RuntimeError("SparseGPT: Cholesky factorisation kept failing after damping retries")
+
+    def prepare_hinv(self, percdamp=0.01):
+        """Returns (Hinv_upper, dead_mask) and releases H (sparsegpt_pruner.py:96-163)."""
+        H = self.H
+        del self.H
+        dead = torch.diag(H) == 0
+        H[dead, dead] = 1
+        H = self._repair_inf(H)
+        damp = percdamp * torch.mean(torch.diag(H))
+        L = self._cholesky_with_damping(H, damp, upper=False)
+        Hi = torch.cholesky_inverse(L)
+        Hi = self._repair_inf(Hi)
+        damp = percdamp * torch.mean(torch.diag(Hi).abs())
+        Hinv = self._cholesky_with_damping(Hi, damp, upper=True)
+        return Hinv.contiguous(), dead
+
+    def fasterprune(self, sparsity, prune_n=0, prune_m=0, blocksize=128, percdamp=0.01):
+        if prune_n != 0:
+            raise NotImplementedError("n:m sparsity is dead code in every shipped ECoFLaP recipe (prune_n = prune_m = 0)")
+        W = self.layer.weight.data.clone()
+        if isinstance(self.layer, nn.Conv2d):
+            W = W.flatten(1)
+        if isinstance(self.layer, _Conv1D):
+            W = W.t()
+        W = W.float().contiguous()
+        Hinv, dead = self.prepare_hinv(percdamp)
+        W[:, dead] = 0
+        kth = []
+        for i1 in range(0, self.columns, blocksize):
+            count = min(i1 + blocksize, self.columns) - i1
+            kth.append(int(self.rows * count * sparsity))  # int(tmp.numel() * sparsity), :187
+        ops.obs_prune(W, Hinv, kth, blocksize)
+        if isinstance(self.layer, _Conv1D):
+            W = W.t()
+        self.layer.weight.data = W.reshape(self.layer.weight.shape).to(self.layer.weight.data.dtype)
+
+    def free(self):
+        self.H = None
+        torch.cuda.empty_cache()
+
+
+__all__ = ["WrappedGPT", "SparseGPT", "math"]

@@ -1,0 +1,259 @@
+"""ECoFLaP stage 1: global importance (zeroth-/first-order) and the per-group sparsity allocation.
+
+Mirror of ``LayerSparsity`` (LAVIS/lavis/compression/pruners/layer_single_base_pruner.py:120-561; the CoOp and
+UPop copies are identical apart from imports) with the same constructor, ``return_sparsity()``,
+``compute_the_sparsity_per_group()`` and ``zo_perturb_parameters()`` seams.
+
+What runs where
+  * the perturbation  w += a*eps*z  is the ``ecf_zo_perturb`` kernel (three roundings reproduced, z drawn by
+    torch after ``torch.manual_seed`` so the RNG stream is the reference's own);
+  * the |W| / W^2 factors of the *Mag* scores are one segmented-reduction launch (``ecf_group_abs_reduce``):
+    sum(|W|*g) == g*sum|W| and sum(W^2 g^2) == g^2 * sum W^2, so per-element score tensors are never built;
+  * the allocator is host arithmetic on <= a few hundred groups and is restated with torch CPU tensors so
+    that the reference's implicit dtype promotions (int64 * float -> fp32, int64 + fp32 -> fp32) and its
+    '+=' overshoot quirk (:301) are reproduced bit for bit.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+class _UniformSparsity:
+    """``uniform_sparsity_module`` (layer_single_base_pruner.py:327-331): any key -> the global ratio."""
+
+    def __init__(self, ratio):
+        self.ratio = ratio
+
+    def __getitem__(self, key):
+        return self.ratio
+
+
+class LayerSparsity:
+    def __init__(self, model, data_loader, loss_func, num_samples, original_sparsity, max_sparsity_per_layer=0.8,
+                 score_method="GradMagSquare_avg", num_noise=1, noise_eps=1e-3, layer_to_group_mapping={},
+                 prune_per_model=False, per_model_group=[]):
+        self.importance_measure = {}
+        self.model = model
+        self.data_loader = data_loader
+        self.loss_func = loss_func
+        self.num_samples = num_samples
+        self.original_sparsity = original_sparsity
+        self.layer_to_group_mapping = layer_to_group_mapping
+        self.max_sparsity_per_layer = max_sparsity_per_layer
+        self.num_noise = num_noise
+        self.noise_eps = noise_eps
+        self.prune_per_model = prune_per_model
+        self.score_method = score_method
+        self.per_model_group = per_model_group
+        if score_method is not None:
+            self.score_compute, self.score_aggregate = score_method.split("_")
+        assert self.max_sparsity_per_layer >= self.original_sparsity
+
+    # ------------------------------------------------------------------ A15 allocator (host)
+    def compute_the_sparsity_per_group(self, total_parameters_to_keep, group_scores, group_num_parameters,
+                                       max_sparsity_per_layer=0.8):
+        """Water-filling allocation, arithmetic identical to layer_single_base_pruner.py:247-314."""
+        target = total_parameters_to_keep
+        score = torch.FloatTensor(list(group_scores.values()))
+        size = torch.LongTensor(list(group_num_parameters.values()))
+        keep_frac = 1 - max_sparsity_per_layer
+
+        # floor guaranteeing the per-group maximum sparsity: ceil(int64 * float) is evaluated in fp32
+        keep = torch.zeros_like(score, dtype=int)
+        keep += torch.ceil(size * keep_frac).int()
+
+        while keep.sum() < target:
+            missing = target - keep.sum()
+            grant = torch.ceil((score / torch.sum(score)) * missing)
+            keep = keep + grant  # int64 + fp32 -> fp32 from the first round on
+            score[keep >= size] = 0  # saturated groups stop competing
+            keep = torch.clamp(keep, max=size)
+
+            if grant.sum() == 0:  # nothing could be granted: hand the shortfall out in index order
+                have = keep.sum()
+                if have < target:
+                    short = target - have
+                    while short > 0:
+                        for g in torch.where(score > 0)[0]:
+                            room = min(short, size[g] - keep[g])
+                            keep[g] += room
+                            short -= room
+                            if short == 0:
+                                break
+
+            if keep.sum() > target:  # overshoot: the reference ADDS the removable amount (sic)
+                excess = keep.sum() - target
+                while excess > 0:
+                    for g in torch.argsort(keep, descending=True, stable=True):
+                        removable = min(excess, keep[g] - (size[g] * keep_frac).int())
+                        keep[g] += removable
+                        excess -= removable
+                        if excess == 0:
+                            break
+
+        return {
+            name: torch.clamp(1 - k / n, min=0, max=1).item()
+            for name, k, n in zip(group_num_parameters.keys(), keep, size)
+        }
+
+    # ------------------------------------------------------------------ A14 + A15 driver
+    def return_sparsity(self):
+        mapping = self.layer_to_group_mapping
+        if self.score_compute.startswith("Real"):
+            raise NotImplementedError(
+                "'Real*' score methods run the 3-iteration global pruning baseline as a ratio oracle "
+                "(layer_single_base_pruner.py:321-325); that baseline is outside the hot path (SURVEY section 8 f, N3)")
+        if mapping is None or len(mapping) == 0:
+            return _UniformSparsity(self.original_sparsity)
+
+        if len(self.importance_measure) == 0:
+            if self.score_compute.startswith("MEZO"):
+                self.importance_measure = self.compute_importance_scores_mezo(mapping)
+            else:
+                self.importance_measure = self.compute_importance_scores(mapping)
+
+        numel = {k: v.numel() for k, v in self.model.named_parameters() if k in mapping}
+        total = sum(numel.values())
+        total_to_keep = int(total * (1 - self.original_sparsity))
+
+        group_scores, group_sizes = {}, {}
+        for layer, group in mapping.items():
+            if group not in group_scores:
+                group_scores[group] = 0
+                group_sizes[group] = 0
+        members = {}
+        for layer, group in mapping.items():
+            members.setdefault(group, []).append(layer)
+        for group, layers in members.items():
+            for layer in layers:
+                group_scores[group] += self.importance_measure[layer].sum()
+                group_sizes[group] += numel[layer]
+            if self.score_aggregate == "avg":
+                group_scores[group] /= group_sizes[group]
+
+        if self.prune_per_model:
+            group_sparsity = {}
+            for prefix in self.per_model_group:
+                sub_scores = {k: v for k, v in group_scores.items() if k.startswith(prefix)}
+                sub_sizes = {k: v for k, v in group_sizes.items() if k.startswith(prefix)}
+                sub_keep = int(sum(list(sub_sizes.values())) * (1 - self.original_sparsity))
+                group_sparsity.update(self.compute_the_sparsity_per_group(
+                    sub_keep, sub_scores, sub_sizes, max_sparsity_per_layer=self.max_sparsity_per_layer))
+        else:
+            group_sparsity = self.compute_the_sparsity_per_group(
+                total_to_keep, group_scores, group_sizes, max_sparsity_per_layer=self.max_sparsity_per_layer)
+
+        kept = sum((1 - group_sparsity[g]) * group_sizes[g] for g in group_sizes)
+        print(kept, total_to_keep)  # the reference's sanity line (:407)
+        return {layer: group_sparsity[group] for layer, group in mapping.items()}
+
+    # ------------------------------------------------------------------ helpers
+    def _selected(self, mapping):
+        names, params = [], []
+        for k, v in self.model.named_parameters():
+            if k in mapping:
+                names.append(k)
+                params.append(v)
+        return names, params
+
+    def _magnitude_sums(self, params):
+        """(sum|w|, sum w^2) per parameter as python floats: one kernel launch over all tensors."""
+        sa, sq = ops.group_abs_reduce([p.data for p in params])
+        return sa.cpu().tolist(), sq.cpu().tolist()
+
+    # ------------------------------------------------------------------ A11 perturbation
+    def zo_perturb_parameters(self, params, random_seed=1, scaling_factor=1, zo_eps=1e-3):
+        """theta <- theta + scaling_factor * z * zo_eps with z ~ N(0, 1) drawn after torch.manual_seed
+        (layer_single_base_pruner.py:473-486); the update itself is the ecf_zo_perturb kernel."""
+        torch.manual_seed(random_seed)
+        for param in params:
+            z = torch.normal(mean=0, std=1, size=param.data.size(), device=param.data.device, dtype=param.data.dtype)
+            data = param.data if param.data.is_contiguous() else param.data.contiguous()
+            ops.zo_perturb(data, z, scaling_factor, zo_eps)
+            if data is not param.data:
+                param.data.copy_(data)
+
+    # ------------------------------------------------------------------ A12 zeroth-order scores
+    def compute_importance_scores_mezo(self, layer_to_group_mapping):
+        model, loss_func = self.model, self.loss_func
+        model.eval()
+        names, params = self._selected(layer_to_group_mapping)
+        device = next(iter(model.parameters())).device
+        eps = self.noise_eps
+        ghat = {k: 0.0 for k in names}
+        for i, (name, param) in enumerate(zip(names, params)):
+            print(i, name)
+            seen = 0
+            for batch in self.data_loader:
+                if seen >= self.num_samples:
+                    break
+                acc = 0.0
+                for _ in range(self.num_noise):
+                    if seen >= self.num_samples:
+                        break
+                    seed = np.random.randint(1000000000)
+                    self.zo_perturb_parameters([param], random_seed=seed, scaling_factor=1, zo_eps=eps)
+                    with torch.no_grad():
+                        loss_plus, batch_len = loss_func(model, batch, device != "cpu")
+                    self.zo_perturb_parameters([param], random_seed=seed, scaling_factor=-2, zo_eps=eps)
+                    with torch.no_grad():
+                        loss_minus, batch_len = loss_func(model, batch, device != "cpu")
+                    # restore (inexact in fp16/bf16 exactly as in the reference)
+                    self.zo_perturb_parameters([param], random_seed=seed, scaling_factor=1, zo_eps=eps)
+                    seen += batch_len
+                    acc += abs(((loss_plus - loss_minus) / (2 * eps)).item())
+                    torch.manual_seed(seed)
+                ghat[name] += acc
+        return self._mezo_scores(names, params, ghat)
+
+    def _mezo_scores(self, names, params, ghat):
+        """layer_single_base_pruner.py:551-559 with the weight factor reduced on the device.  Values are
+        1-element fp32 tensors holding sum(score) -- the only thing return_sparsity reads."""
+        g = {k: torch.FloatTensor([ghat[k]]).abs() for k in names}
+        if self.score_compute == "MEZO-GradOnly":
+            return {k: g[k].abs() for k in names}
+        sum_abs, sum_sq = self._magnitude_sums(params)
+        if self.score_compute == "MEZO-GradMagAbs":
+            return {k: torch.FloatTensor([sum_abs[i]]) * g[k].abs() for i, k in enumerate(names)}
+        if self.score_compute == "MEZO-GradMagSquare":
+            return {k: torch.FloatTensor([sum_sq[i]]) * g[k] ** 2 for i, k in enumerate(names)}
+        raise ValueError(f"unknown zeroth-order score method {self.score_compute!r}")
+
+    # ------------------------------------------------------------------ A13 first-order scores
+    def compute_importance_scores(self, layer_to_group_mapping):
+        """mean over batches of |dL/dW| (or g^2), then |W|*|g| / W^2*g / |g| (:416-471).  Gradients stay on the
+        device (the reference copies 3.7 G fp32 elements to the host per batch); only sum(score) is kept."""
+        model, loss_func = self.model, self.loss_func
+        names, params = self._selected(layer_to_group_mapping)
+        device = next(iter(model.parameters())).device
+        acc = {k: None for k in names}
+        seen, nbatches = 0, 0
+        for batch in self.data_loader:
+            if seen >= self.num_samples:
+                break
+            loss, batch_len = loss_func(model, batch, device != "cpu")
+            seen += batch_len
+            nbatches += 1
+            grads = torch.autograd.grad(loss, params)
+            assert len(grads) == len(names) == len(params)
+            for k, gr in zip(names, grads):
+                gr = gr.detach().float()
+                term = gr * gr if self.score_compute == "GradMagSquare" else gr.abs()
+                acc[k] = term if acc[k] is None else acc[k].add_(term)
+        scores = {}
+        for k, p in zip(names, params):
+            gbar = acc[k] / nbatches
+            w = p.detach().float()
+            if "GradMagSquare" in self.score_compute:
+                s = (w * w * gbar).sum()
+            elif "GradMagAbs" in self.score_compute:
+                s = (w.abs() * gbar.abs()).sum()
+            elif "GradOnly" in self.score_compute:
+                s = gbar.abs().sum()
+            else:
+                raise ValueError(f"unknown first-order score method {self.score_compute!r}")
+            scores[k] = s.reshape(1).cpu()
+        return scores

@@ -1,0 +1,160 @@
+"""End-to-end: the product pruner classes (reference names / kwargs) on a B200 against fixtures produced by the
+UNMODIFIED reference classes on the same tiny models and batches (tests/gen_golden_e2e.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import e2e_cases as cases  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load("tests/golden/e2e_pruners.npz")
+
+
+def _compare(model, gold, prefix, min_agree, weight_rtol=None, later_agree=None):
+    """later_agree: looser mask agreement for blocks > 0 of the SparseGPT cases -- their inputs already differ
+    (cuSOLVER vs LAPACK factorisations of block 0) and OBS amplifies that; block 0 sees identical inputs."""
+    state = cases.prunable_state(model)
+    checked = 0
+    for k, got in state.items():
+        key = f"{prefix}__{k}"
+        if key not in gold.files:
+            continue
+        ref = gold[key]
+        if (ref == 0).mean() < 0.05:
+            assert (got == 0).mean() < 0.05, k  # layer the reference left dense
+            continue
+        checked += 1
+        agree = ((got == 0) == (ref == 0)).mean()
+        first_block = ".0." in k.split("weight")[0][-16:] or "blocks.0." in k
+        need = min_agree if (later_agree is None or first_block) else later_agree
+        assert agree >= need, (k, agree)
+        # identical pruned COUNT: the selection rule (k per row / idx+1 per layer) is bit exact even when a
+        # near-tie flips because the GPU forward rounds differently from the CPU forward
+        assert abs(int((got == 0).sum()) - int((ref == 0).sum())) <= max(2, int(2e-4 * ref.size)), k
+        if weight_rtol is not None and first_block:
+            same = (got == 0) == (ref == 0)
+            rel = np.linalg.norm((got - ref)[same]) / max(np.linalg.norm(ref), 1e-12)
+            assert rel < weight_rtol, (k, rel)
+    assert checked > 0
+    return checked
+
+
+def test_vit_wanda_matches_reference(gold):
+    from ecoflap_b200.compression import load_pruner
+
+    m = cases.vit_model().cuda()
+    p = load_pruner("vit_wanda_pruner", m, cases.vit_loader(), cfg=dict(prune_spec="3-0.5-1.0-1.0", num_samples=16,
+                                                                       model_prefix="visual"))
+    model, sd = p.prune()
+    assert model is m and sd[("anything")] == 0.5  # uniform_sparsity_module behaviour
+    assert _compare(m, gold, "vit_wanda", 0.995) == 12
+
+
+def test_t5_wanda_matches_reference(gold):
+    from ecoflap_b200.compression import load_pruner
+
+    m = cases.t5_model().cuda()
+    p = load_pruner("t5_wanda_pruner", m, cases.t5_loader(), cfg=dict(prune_spec="2-0.5-1.0-1.0", num_samples=16,
+                                                                     model_prefix="t5_model"))
+    p.prune()
+    assert _compare(m, gold, "t5_wanda", 0.995) == 2 * 7 + 2 * 11
+    assert p.check_sparsity(m, "t5_model.encoder.block") == pytest.approx(0.5, abs=1e-6)
+
+
+def test_blip2_wanda_with_reference_ratios(gold, tmp_path):
+    """Stage 2 under the ratios the reference's zeroth-order stage 1 produced (the --sparsity_dict re-entry
+    path, wanda_pruner.py:721-725).  Stage 1 itself draws z from the device RNG, so it is only comparable on
+    the same device."""
+    import yaml
+
+    from ecoflap_b200.compression import load_pruner
+
+    sd = {str(k): float(v) for k, v in zip(gold["blip2_ecoflap__sparsity_keys"], gold["blip2_ecoflap__sparsity_vals"])}
+    path = tmp_path / "ratios.yaml"
+    path.write_text(yaml.dump(sd))
+    m = cases.blip2_model().cuda()
+    p = load_pruner("blipt5_wanda_pruner", m, cases.blip2_loader(), cfg=dict(
+        t5_prune_spec="2-0.5-1.0-1.0", vit_prune_spec="3-0.5-1.0-1.0", t5_pruning_method="x", vit_pruning_method="x",
+        num_samples=16, sparsity_ratio_granularity="block", max_sparsity_per_layer=0.6, sparsity_dict=str(path)))
+    p.prune()
+    _compare(m, gold, "blip2_ecoflap", 0.99)
+
+
+def test_blip2_ecoflap_zeroth_order_runs_and_allocates():
+    """Full coarse-to-fine path on the device: zeroth-order scores -> allocation -> Wanda."""
+    from ecoflap_b200.compression import load_pruner
+
+    np.random.seed(42)
+    m = cases.blip2_model().cuda()
+    p = load_pruner("blipt5_wanda_pruner", m, cases.blip2_loader(), cfg=dict(
+        t5_prune_spec="2-0.5-1.0-1.0", vit_prune_spec="3-0.5-1.0-1.0", t5_pruning_method="x", vit_pruning_method="x",
+        num_samples=16, sparsity_ratio_granularity="block", max_sparsity_per_layer=0.6,
+        score_method="MEZO-GradOnly_sum", num_data_first_stage=8, num_noise=1, noise_eps=1e-3))
+    _, sd = p.prune()
+    vals = np.array(list(sd.values()))
+    assert len(sd) == 3 * 4 + 2 * 7 + 2 * 11 and vals.min() >= 0.0 and vals.max() <= 0.6 + 1e-6
+    sizes = {k: v.numel() for k, v in m.named_parameters() if k in sd}
+    overall = sum(sd[k] * sizes[k] for k in sd) / sum(sizes.values())
+    assert overall == pytest.approx(0.5, abs=2e-3)
+    zeros = sum(int((v == 0).sum()) for k, v in m.named_parameters() if k in sd)
+    assert zeros / sum(sizes.values()) == pytest.approx(0.5, abs=5e-3)
+
+
+def test_clip_wanda_matches_reference(gold):
+    from ecoflap_b200.pruners import CLIPLayerWandaPruner
+    from ecoflap_b200.synthetic import clip_forward_to_cache
+
+    m = cases.clip_model().cuda()
+    p = CLIPLayerWandaPruner(model=m, data_loader=cases.clip_loader(), language_prune_spec="1-0.6-1-1",
+                             visual_prune_spec="1-0.6-1-1", num_samples=16)
+    p.forward_to_cache = clip_forward_to_cache(cases.clip_class_tokens())
+    p.prune()
+    assert _compare(m, gold, "clip_wanda", 0.99) == 2 * 4 + 2 * 4
+    assert not hasattr(m.visual.transformer.resblocks[0], "hacky_attn")
+
+
+def test_vit_sparsegpt_matches_reference(gold):
+    from ecoflap_b200.compression import load_pruner
+
+    m = cases.vit_model().cuda()
+    p = load_pruner("vit_sparsegpt_pruner", m, cases.vit_loader(batch=1, n=48), cfg=dict(
+        prune_spec="3-0.6-1.0-1.0", num_samples=48, model_prefix="visual"))
+    p.prune()
+    _compare(m, gold, "vit_sparsegpt", 0.97, weight_rtol=5e-2, later_agree=0.85)
+
+
+def test_clip_sparsegpt_matches_reference(gold):
+    from ecoflap_b200.pruners import CLIPLayerSparseGPTPruner
+    from ecoflap_b200.synthetic import clip_forward_to_cache
+
+    m = cases.clip_model().cuda()
+    p = CLIPLayerSparseGPTPruner(model=m, data_loader=cases.clip_loader(), language_prune_spec="1-0.6-1-1",
+                                 visual_prune_spec="1-0.6-1-1", num_samples=16)
+    p.forward_to_cache = clip_forward_to_cache(cases.clip_class_tokens())
+    p.prune()
+    _compare(m, gold, "clip_sparsegpt", 0.95, weight_rtol=1e-1, later_agree=0.85)
+
+
+def test_fp16_bf16_models_run():
+    """Half-precision paths (the real configurations): fp16 ViT under autocast, bf16 T5."""
+    from ecoflap_b200 import synthetic as syn
+    from ecoflap_b200.compression import load_pruner
+
+    m = syn.init_weights_(syn.EvaClipModel(num_classes=16, autocast_dtype=torch.float16, **cases.VIT_KW), seed=1).cuda().half().eval()
+    load_pruner("vit_wanda_pruner", m, cases.vit_loader(), cfg=dict(prune_spec="3-0.5-1.0-1.0", num_samples=16,
+                                                                   model_prefix="visual")).prune()
+    z = [(p == 0).float().mean().item() for n, p in m.named_parameters() if p.dim() == 2 and ".blocks." in n]
+    assert all(abs(v - 0.5) < 2e-3 for v in z)
+    t5 = syn.init_weights_(syn.T5Model(autocast=True, **cases.T5_KW), seed=3).cuda().bfloat16().eval()
+    load_pruner("t5_wanda_pruner", t5, cases.t5_loader(), cfg=dict(prune_spec="2-0.5-1.0-1.0", num_samples=16,
+                                                                  model_prefix="t5_model")).prune()
+    z = [(p == 0).float().mean().item() for n, p in t5.named_parameters() if p.dim() == 2 and ".block." in n and "relative" not in n]
+    assert all(v == 0.5 for v in z)

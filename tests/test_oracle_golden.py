@@ -127,3 +127,19 @@ def test_obs_prune_matches_reference(golden):
         rel = np.linalg.norm(Wout - ref) / np.linalg.norm(ref)
         assert rel <= 2e-2, (name, rel)  # LAPACK builds differ (numpy/OpenBLAS vs torch/MKL)
         assert abs((ref == 0).mean() - (Wout == 0).mean()) < 2e-3
+
+
+def test_select_steps_match_reference_prune_loop(golden):
+    """(W_before, scaler_row) captured inside the reference's own _prune loops (tests/gen_golden_e2e.py) ->
+    the oracle's select must reproduce the reference's pruned weights bit for bit."""
+    g = golden("e2e_pruners")
+    for i in range(int(g["vit_wanda__nsteps"])):  # per-LAYER threshold, wanda_pruner.py:553-558
+        W, s, ref = g[f"vit_wanda__step{i}__W"], g[f"vit_wanda__step{i}__s"], g[f"vit_wanda__step{i}__Wafter"]
+        got, mask, _ = orc.wanda_prune_layer(W, s, 0.5)
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), i
+        assert mask.sum() >= int(W.size * 0.5) + 1
+    for i in range(int(g["t5_wanda__nsteps"])):  # per-ROW stable sort, wanda_pruner.py:272-279
+        W, s, ref = g[f"t5_wanda__step{i}__W"], g[f"t5_wanda__step{i}__s"], g[f"t5_wanda__step{i}__Wafter"]
+        got, mask = orc.wanda_prune_rows(W, s, 0.5)
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), i
+        assert (mask.sum(axis=1) == int(W.shape[1] * 0.5)).all()
