@@ -486,10 +486,16 @@ def text_batches(n, batch, src_len, tgt_len, vocab, seed=0, with_image=None):
 
 
 def init_weights_(model, std=0.02, seed=0):
-    """N(0, 0.02^2) for every matrix (SURVEY 8d synthetic inputs), deterministic."""
+    """N(0, 0.02^2) for every matrix (SURVEY 8d synthetic inputs), deterministic.  LayerNorm gains/biases are
+    randomised too: with the default (1, 0) affine every LayerNorm output sums to zero over the channels, which
+    makes the SparseGPT Hessian of the following Linear exactly singular -- trained models never are."""
     g = torch.Generator().manual_seed(seed)
     with torch.no_grad():
         for p in model.parameters():
             if p.dim() >= 2:
                 p.copy_(torch.randn(p.shape, generator=g) * std)
+        for m in model.modules():
+            if isinstance(m, nn.LayerNorm) and m.elementwise_affine:
+                m.weight.copy_(1.0 + 0.3 * torch.randn(m.weight.shape, generator=g))
+                m.bias.copy_(0.3 * torch.randn(m.bias.shape, generator=g))
     return model

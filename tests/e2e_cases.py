@@ -42,12 +42,12 @@ def clip_model():
 
 
 def clip_loader(batch=4, n=16):
-    return syn.image_batches(n, batch, 32, classes=8, seed=8, key="img")
+    return syn.image_batches(n, batch, 32, classes=64, seed=8, key="img")
 
 
 def clip_class_tokens():
     g = torch.Generator().manual_seed(9)
-    t = torch.randint(1, 200, (8, 16), generator=g)
+    t = torch.randint(1, 200, (64, 16), generator=g)
     t[:, 10] = 255  # argmax position = "EOT" token
     return t
 

@@ -105,8 +105,8 @@ def main():
 
     # 6. CLIP (CoOp), SparseGPT 40 %
     m = cases.clip_model()
-    p = coop.sparsegpt.CLIPLayerSparseGPTPruner(model=m, data_loader=cases.clip_loader(), language_prune_spec="1-0.6-1-1",
-                                                visual_prune_spec="1-0.6-1-1", num_samples=16)
+    p = coop.sparsegpt.CLIPLayerSparseGPTPruner(model=m, data_loader=cases.clip_loader(n=96), language_prune_spec="1-0.6-1-1",
+                                                visual_prune_spec="1-0.6-1-1", num_samples=96)
     p.forward_to_cache = clip_forward_to_cache(cases.clip_class_tokens())
     p.prune()
     for k, v in cases.prunable_state(m).items():
