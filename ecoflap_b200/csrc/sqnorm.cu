@@ -8,7 +8,8 @@
 // row lanes; grid.x tiles the channels, grid.y splits the tokens so that ~4 CTAs per SM are in
 // flight.  Each CTA writes one partial row into the workspace; the last CTA to finish a channel
 // tile (atomic ticket) adds the partials in a fixed order, so the result is deterministic, and
-// applies   scaler_row = scaler_row * rescale + sum * inv_n.
+// applies   scaler_row = scaler_row * rescale + sum * inv_n.  The tickets reset themselves, so the first
+// 4 KB of the workspace must be zero before the FIRST call only (no per-call memset node).
 // Bound: HBM.  Algorithmic bytes per call: T*C*sizeof(x) + 8*C.
 #include "common.cuh"
 
@@ -165,7 +166,6 @@ static int launch_sqnorm(const void* x, int64_t T, int64_t C, int64_t ld, float*
               "sqnorm: workspace %zu < %zu bytes", ws_bytes, need);
   unsigned* counters = reinterpret_cast<unsigned*>(ws);
   float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + kSqCounterBytes);
-  ECF_CUDA_OK(cudaMemsetAsync(counters, 0, p.nx * sizeof(unsigned), stream));
   dim3 grid((unsigned)p.nx, (unsigned)p.splits), block(kSqTX, kSqTY);
   if (vec)
     sqnorm_kernel<DT, true><<<grid, block, 0, stream>>>(x, T, C, ld, p.rows_per_cta, partial, p.cpad, counters,

@@ -1,0 +1,93 @@
+"""Multi-GPU partitioning of the hot path (new design -- the reference runs on one GPU).
+
+One process per GPU, ``torch.distributed`` (NCCL over NVLink/NVSwitch on the box, gloo in the CPU tests):
+
+  * calibration batches are sharded round-robin over the ranks; every rank accumulates the running mean of
+    sum x^2 (or the Hessian) over ITS samples; one all-reduce per block over the concatenated per-Linear
+    vectors turns them into the global mean  sum_r n_r * s_r / sum_r n_r  (latency bound: <= 35 k floats);
+  * per-ROW mask selection is sharded over output rows (rows are independent): rank r selects rows
+    [r*R/P, (r+1)*R/P) in place and an all-gather rebuilds the pruned matrix on every rank;
+  * the per-LAYER threshold select and the OBS sweep are replicated (their exchange steps are future work).
+
+The collective plumbing below works on CPU and CUDA tensors alike; the kernels are only reached through the
+``select_rows`` callable, so the world-size-2 gloo tests exercise exactly this code.
+"""
+from __future__ import annotations
+
+from typing import Callable, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def is_dist() -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def rank_world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def shard_indices(n: int, rank: int, world: int):
+    """Round-robin ownership of calibration batches: j = rank (mod world)."""
+    return list(range(rank, n, world))
+
+
+def row_range(rows: int, rank: int, world: int):
+    """Contiguous, equal row shards (requires rows % world == 0 for the in-place all-gather)."""
+    per = rows // world
+    return rank * per, (rank + 1) * per
+
+
+def allreduce_running_means(stats: Sequence[torch.Tensor], counts: Sequence[int], group=None):
+    """In place: every tensor in ``stats`` (a per-rank running mean over ``counts[i]`` samples) becomes the
+    mean over the samples of all ranks.  One all-reduce for the whole list.  Returns the global counts."""
+    if not stats:
+        return []
+    flat = torch.cat([(s.reshape(-1) * float(n)) for s, n in zip(stats, counts)])
+    tail = torch.tensor([float(n) for n in counts], dtype=flat.dtype, device=flat.device)
+    buf = torch.cat([flat, tail])
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    totals = buf[flat.numel():]
+    off = 0
+    out_counts = []
+    for i, s in enumerate(stats):
+        n = s.numel()
+        tot = totals[i]
+        s.copy_((buf[off:off + n] / tot).reshape(s.shape))
+        off += n
+        out_counts.append(int(round(float(tot))))
+    return out_counts
+
+
+def sync_block_norms(accumulators, group=None):
+    """accumulators: WrappedGPT-like objects (.scaler_row fp32 [C], .nsamples)."""
+    accs = list(accumulators)
+    totals = allreduce_running_means([a.scaler_row for a in accs], [a.nsamples for a in accs], group)
+    for a, n in zip(accs, totals):
+        a.nsamples = n
+
+
+def sync_block_hessians(accumulators, group=None):
+    accs = list(accumulators)
+    totals = allreduce_running_means([a.H for a in accs], [a.nsamples for a in accs], group)
+    for a, n in zip(accs, totals):
+        a.nsamples = n
+
+
+def row_sharded_select(W: torch.Tensor, select_rows: Callable[[torch.Tensor], None], group=None):
+    """Prune this rank's row shard of W in place with ``select_rows(shard)`` and all-gather the shards so
+    every rank ends up with the fully pruned matrix.  Falls back to replicated selection when the rows do not
+    divide evenly."""
+    rank, world = rank_world(group)
+    R = W.shape[0]
+    if world == 1 or R % world != 0 or not W.is_contiguous():
+        select_rows(W)
+        return W
+    r0, r1 = row_range(R, rank, world)
+    shard = W[r0:r1]
+    select_rows(shard)
+    dist.all_gather_into_tensor(W, shard.clone(), group=group)
+    return W

@@ -39,8 +39,9 @@ class _Workspaces:
     def __init__(self):
         self._bufs = {}
 
-    def get(self, device, nbytes: int) -> torch.Tensor:
-        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    def get(self, device, nbytes: int, tag: str = "") -> torch.Tensor:
+        # one buffer per op family: some kernels keep self-resetting counters at the start of their workspace
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream, tag)
         buf = self._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = torch.zeros(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
@@ -68,7 +69,7 @@ def sqnorm_accum(x: torch.Tensor, scaler_row: torch.Tensor, rescale: float, inv_
     x2, T, C, ld = _as_2d(x)
     assert scaler_row.numel() == C
     need = lib.ecf_workspace_bytes(_abi.OP_SQNORM, T, C)
-    ws = _ws.get(x.device, need)
+    ws = _ws.get(x.device, need, "sqnorm")
     check(lib.ecf_sqnorm_accum(x2.data_ptr(), dtype_code(x2), T, C, ld, scaler_row.data_ptr(), float(rescale),
                                float(inv_n), ws.data_ptr(), ws.numel(), _stream(x)))
 
@@ -109,7 +110,7 @@ def wanda_layer_thresh_apply(W, scaler_row, kth_index: int, thres_out=None, mask
     if not (0 <= kth_index < R * C):
         raise IndexError(f"index {kth_index} is out of bounds for dimension 0 with size {R * C}")
     need = lib.ecf_workspace_bytes(_abi.OP_LAYER_THRESH, R, C)
-    ws = _ws.get(W.device, need)
+    ws = _ws.get(W.device, need, "layer_thresh")
     check(lib.ecf_wanda_layer_thresh_apply(
         W.data_ptr(), dtype_code(W), R, C, ld, scaler_row.data_ptr(), int(kth_index),
         thres_out.data_ptr() if thres_out is not None else None,
@@ -158,7 +159,7 @@ def group_abs_reduce(tensors):
     sum_abs = torch.zeros(n, dtype=torch.float64, device=dev)
     sum_sq = torch.zeros(n, dtype=torch.float64, device=dev)
     need = lib.ecf_workspace_bytes(_abi.OP_GROUP_REDUCE, n, cb)
-    ws = _ws.get(dev, need)
+    ws = _ws.get(dev, need, "group_reduce")
     check(lib.ecf_group_abs_reduce(d_table.data_ptr(), n, cb, sum_abs.data_ptr(), sum_sq.data_ptr(), ws.data_ptr(),
                                    ws.numel(), _stream(tensors[0])))
     return sum_abs, sum_sq
@@ -171,7 +172,7 @@ def hessian_accum(x: torch.Tensor, H: torch.Tensor, alpha: float, beta: float) -
     x2, T, C, ld = _as_2d(x)
     assert H.shape[0] == C and H.shape[1] == C
     need = lib.ecf_workspace_bytes(_abi.OP_HESSIAN, T if x2.dtype == torch.float32 else 0, C)
-    ws = _ws.get(x.device, need)
+    ws = _ws.get(x.device, need, "hessian")
     check(lib.ecf_hessian_accum(x2.data_ptr(), dtype_code(x2), T, C, ld, H.data_ptr(), H.stride(0), float(alpha),
                                 float(beta), ws.data_ptr(), ws.numel(), _stream(x)))
 
@@ -186,6 +187,6 @@ def obs_prune(W: torch.Tensor, Hinv: torch.Tensor, kth_per_block, blocksize: int
     assert len(kth_per_block) == nb
     arr = (ctypes.c_int64 * nb)(*[int(v) for v in kth_per_block])
     need = lib.ecf_workspace_bytes(_abi.OP_OBS, R, C)
-    ws = _ws.get(W.device, need)
+    ws = _ws.get(W.device, need, "obs")
     check(lib.ecf_obs_prune(W.data_ptr(), R, C, ldw, Hinv.data_ptr(), Hinv.stride(0), arr, int(blocksize),
                             ws.data_ptr(), ws.numel(), _stream(W)))

@@ -75,7 +75,8 @@ ECF_API size_t ecf_workspace_bytes(int op, int64_t R, int64_t C);
  * (CoOp/trainers/pruners/wanda_pruner.py:159-172, UPop/pruners/wanda_pruner.py:65-78).
  *   scaler_row[c] = scaler_row[c] * rescale + (sum_t x[t,c]^2) * inv_n
  * x is the hook input flattened to [T, C]; the host passes rescale = n/(n+B), inv_n = 1/(n+B).
- * fp32 accumulation, deterministic summation order. */
+ * fp32 accumulation, deterministic summation order.  The first 4 KB of `ws` hold self-resetting tickets: zero
+ * them once before the first call and do not share this workspace with other ops. */
 ECF_API int ecf_sqnorm_accum(const void* x, int x_dtype, int64_t T, int64_t C, int64_t ld,
                      float* scaler_row, float rescale, float inv_n,
                      void* ws, size_t ws_bytes, ecf_stream_t stream);
