@@ -1,4 +1,8 @@
-// A3+A4+A7 -- fused Wanda score / per-row k-smallest select / in-place apply.
+// A3+A4+A7 -- fused Wanda score / per-row k-smallest select / in-place apply: C-ABI entry + GENERIC kernel.
+//
+// Aligned rows (C % 8 == 0, 16-byte aligned) -- every shape of the BASELINE.json configurations -- take the
+// coarse-to-fine kernel in row_select_fast.cuh.  The kernel below is the shape-generic path (ragged C,
+// unaligned views): a plain 31-round bisection on 32-bit keys, bit-exact but far from the HBM roofline.
 //
 // Replaces  W_metric = |W| * sqrt(scaler_row);  sort(W_metric, dim=-1, stable=True);
 //           indices[:, :k];  scatter_;  W[mask] = 0
@@ -15,6 +19,8 @@
 // Ties at the threshold are resolved by ascending column index with a group-wide prefix scan, which
 // reproduces torch.sort(stable=True)[:, :k] exactly.
 // Bound: HBM.  Algorithmic bytes per call: 2*R*C*sizeof(w) + 4*C.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ecf {
@@ -301,6 +307,17 @@ static int run_row_select(void* W, int64_t R, int64_t C, int64_t ld, const float
   return dispatch_nv<DT, false>(nv, W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
 }
 
+int row_select_fast_f16(void*, int64_t, int64_t, int64_t, const float*, int64_t, int, uint8_t*, int64_t, unsigned long long*, cudaStream_t);
+int row_select_fast_bf16(void*, int64_t, int64_t, int64_t, const float*, int64_t, int, uint8_t*, int64_t, unsigned long long*, cudaStream_t);
+int row_select_fast_f32(void*, int64_t, int64_t, int64_t, const float*, int64_t, int, uint8_t*, int64_t, unsigned long long*, cudaStream_t);
+
+// tuning / A-B switches (read once): ECF_RS_NVMAX = vectors per lane cap of the fast kernel (1..8),
+// ECF_RS_GENERIC=1 forces the generic kernel.
+static int rs_env(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v != nullptr && *v ? atoi(v) : dflt;
+}
+
 }  // namespace ecf
 
 extern "C" int ecf_wanda_row_select_apply(void* W, int w_dtype, int64_t R, int64_t C, int64_t ld,
@@ -320,6 +337,17 @@ extern "C" int ecf_wanda_row_select_apply(void* W, int w_dtype, int64_t R, int64
   if (R == 0) return ECF_OK;
   if (k_per_row > C) k_per_row = C;  // sort_res[1][:, :k] clamps like python slicing
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  static const int nv_max = [] { int v = rs_env("ECF_RS_NVMAX", 8); return v < 1 ? 1 : (v > 8 ? 8 : v); }();
+  static const bool force_generic = rs_env("ECF_RS_GENERIC", 0) != 0;
+  const int vec = w_dtype == ECF_F32 ? 4 : 8;
+  const bool aligned = (C % 8 == 0) && (ld % vec == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  if (aligned && !force_generic && C <= 32768 && w_dtype >= 0 && w_dtype <= 2) {
+    switch (w_dtype) {
+      case ECF_F32: return row_select_fast_f32(W, R, C, ld, scaler_row, k_per_row, nv_max, mask_bits, mask_ld, n_zero, s);
+      case ECF_F16: return row_select_fast_f16(W, R, C, ld, scaler_row, k_per_row, nv_max, mask_bits, mask_ld, n_zero, s);
+      case ECF_BF16: return row_select_fast_bf16(W, R, C, ld, scaler_row, k_per_row, nv_max, mask_bits, mask_ld, n_zero, s);
+    }
+  }
   switch (w_dtype) {
     case ECF_F32: return run_row_select<ECF_F32>(W, R, C, ld, scaler_row, k_per_row, mask_bits, mask_ld, n_zero, s);
     case ECF_F16: return run_row_select<ECF_F16>(W, R, C, ld, scaler_row, k_per_row, mask_bits, mask_ld, n_zero, s);

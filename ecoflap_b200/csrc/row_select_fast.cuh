@@ -1,0 +1,424 @@
+// A3+A4+A7 -- fused Wanda score / per-row k-smallest select / in-place apply: the HBM-roofline path.
+//
+// Replaces  W_metric = |W| * sqrt(scaler_row);  sort(W_metric, dim=-1, stable=True);  indices[:, :k];
+//           scatter_;  W[mask] = 0
+// (LAVIS/lavis/compression/pruners/wanda_pruner.py:260,272-279; CoOp wanda_pruner.py:357,379-383;
+//  UPop wanda_pruner.py:243,253-260; LLaMA/image_classifiers/prune_utils.py:35-38).
+//
+// Budget.  At 6.5 TB/s a 16-bit row element (read + write) may cost ~22 issue slots per SM-clock
+// across both ALU pipes, so a 31-round bisection on 32-bit keys (2 ops per element per round) cannot keep
+// up.  The select is therefore coarse-to-fine:
+//   * every element's exact fp32 score is computed once; its upper 16 bits (clamped to 0x7bff so that
+//     the pattern is a finite fp16 number) are kept PACKED two per register.  Comparing such patterns
+//     as fp16 values equals comparing them as integers, so one HSET2 + one HADD2 counts two elements
+//     against a pivot: 1 op per element per pass.
+//   * a 32-sample in-warp bitonic sort seeds a bracket [lo, hi) around the k-th coarse key; offset
+//     interpolation passes (aiming M/3 elements either side of rank k, bisection when a pass fails to
+//     halve the bracket) shrink it until it holds <= M elements or a single coarse value (4-7 passes).
+//   * only the elements inside the bracket are ranked exactly by (fp32 key, column), which reproduces
+//     torch.sort(stable=True)[:, :k] bit for bit.  Heavy ties (thousands of equal coarse keys, e.g.
+//     already-pruned weights) take a slower in-register bisection on the low key bits and the column.
+// sqrt(scaler_row) is computed once per CTA into shared memory (CTAs are persistent over rows).
+// One GROUP of G lanes (32 ... 512) owns a row; a lane holds NV 8-element vectors of it.
+// Bound: HBM.  Algorithmic bytes per call: 2*R*C*sizeof(w) + 4*C.
+#pragma once
+
+#include "common.cuh"
+
+namespace ecf {
+
+constexpr int kRfMaxWarps = 16;   // warps per row group (G <= 512)
+constexpr int kRfMaxGroups = 8;   // row groups per CTA (G >= 32, CTA of 256 threads)
+constexpr int kRfCap = 256;       // exact-ranking capacity per row
+constexpr int kRfBand = 32;       // stop narrowing once the bracket holds this many elements
+constexpr uint32_t kRfInf = 0x7c00u;  // fp16 +inf pattern: sorts after every real coarse key
+
+struct RfShared {
+  int slots[2][kRfMaxGroups][kRfMaxWarps];
+  uint32_t seed[kRfMaxGroups][2];
+  unsigned long long thr[kRfMaxGroups];
+  int cand_n[kRfMaxGroups];
+  unsigned long long cand[kRfMaxGroups][kRfCap];  // key << 32 | column
+};
+
+__device__ __forceinline__ __half2 rf_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t rf_dup(uint32_t p) { return p | (p << 16); }
+
+template <bool MULTI>
+__device__ __forceinline__ void rf_gsync(int group, int G) {
+  if constexpr (MULTI) named_bar_sync(1 + group, G);
+  else __syncwarp();
+}
+
+// sum of a (packed) int over the G lanes of a row group
+template <bool MULTI>
+__device__ __forceinline__ int rf_gsum(int v, int G, int group, int wig, int lane, RfShared& sh, int& parity) {
+  const int w = warp_sum(v);
+  if constexpr (!MULTI) return w;
+  int* s = sh.slots[parity][group];
+  if (lane == 0) s[wig] = w;
+  named_bar_sync(1 + group, G);
+  parity ^= 1;
+  int tot = 0;
+  const int nw = G >> 5;
+  for (int j = 0; j < nw; ++j) tot += s[j];
+  return tot;
+}
+
+// number of packed coarse keys below the pivot (both halves): one HSET2 + one HADD2 per TWO elements
+template <int NP>
+__device__ __forceinline__ int rf_count1(const uint32_t (&co)[NP], uint32_t pivot) {
+  const __half2 pv = rf_h2(rf_dup(pivot));
+  __half2 a0 = rf_h2(0u), a1 = rf_h2(0u);
+#pragma unroll
+  for (int p = 0; p < NP; p += 2) {
+    a0 = __hadd2(a0, __hlt2(rf_h2(co[p]), pv));
+    a1 = __hadd2(a1, __hlt2(rf_h2(co[p + 1]), pv));
+  }
+  const float2 f = __half22float2(__hadd2(a0, a1));
+  return (int)(f.x + f.y);
+}
+
+template <int NP>
+__device__ __forceinline__ int rf_count2(const uint32_t (&co)[NP], uint32_t lo, uint32_t hi) {
+  const __half2 pl = rf_h2(rf_dup(lo)), ph = rf_h2(rf_dup(hi));
+  __half2 a0 = rf_h2(0u), a1 = rf_h2(0u), b0 = rf_h2(0u), b1 = rf_h2(0u);
+#pragma unroll
+  for (int p = 0; p < NP; p += 2) {
+    a0 = __hadd2(a0, __hlt2(rf_h2(co[p]), pl));
+    b0 = __hadd2(b0, __hlt2(rf_h2(co[p]), ph));
+    a1 = __hadd2(a1, __hlt2(rf_h2(co[p + 1]), pl));
+    b1 = __hadd2(b1, __hlt2(rf_h2(co[p + 1]), ph));
+  }
+  const float2 fa = __half22float2(__hadd2(a0, a1)), fb = __half22float2(__hadd2(b0, b1));
+  return (int)(fa.x + fa.y) | ((int)(fb.x + fb.y) << 16);
+}
+
+__device__ __forceinline__ uint32_t rf_coarse_pair(float w0, float w1, float q0, float q1) {
+  const uint32_t b0 = min(__float_as_uint(__fmul_rn(fabsf(w0), q0)), 0x7bffffffu);
+  const uint32_t b1 = min(__float_as_uint(__fmul_rn(fabsf(w1), q1)), 0x7bffffffu);
+  return __byte_perm(b0, b1, 0x7632);  // (b1 >> 16) << 16 | (b0 >> 16)
+}
+
+// Lane-local walk over the bracket elements recorded in `bm` (bit e = element e of this lane: vector e >> 3,
+// slot e & 7).  The weight is re-read from global memory (an L1/L2 hit: this lane has just streamed the row), so
+// no register array is indexed dynamically and the code stays small.
+//   MODE 0: append (key, column) to the shared candidate list
+//   MODE 1: count keys < a                    MODE 2: count keys == a with column < b
+//   MODE 3: zero the element when (key, column) <= thr; patch the packed mask; count new zeros
+template <int DT, int MODE>
+__device__ __forceinline__ int rf_walk(unsigned long long bm, char* wrow, const float* qtab, int G, int gl, uint32_t a, uint32_t b,
+                                       unsigned long long thr, unsigned long long* cand, int* cand_n, uint8_t* mask_row) {
+  int c = 0;
+  while (bm) {
+    const int e = __ffsll((long long)bm) - 1;
+    bm &= bm - 1;
+    const uint32_t col = (uint32_t)(((e >> 3) * G + gl) * 8 + (e & 7));
+    const float w = load_elem<DT>(wrow, col);
+    const uint32_t key = score_key(wanda_score(w, qtab[col]));
+    if constexpr (MODE == 0) {
+      cand[atomicAdd(cand_n, 1)] = ((unsigned long long)key << 32) | col;
+    } else if constexpr (MODE == 1) {
+      c += key < a ? 1 : 0;
+    } else if constexpr (MODE == 2) {
+      c += (key == a && col < b) ? 1 : 0;
+    } else {
+      if ((((unsigned long long)key << 32) | col) <= thr) {
+        store_zero<DT>(wrow, col);
+        if (mask_row != nullptr) mask_row[col >> 3] |= (uint8_t)(1u << (col & 7));
+        c += w != 0.f ? 1 : 0;
+      }
+    }
+  }
+  return c;
+}
+
+template <int DT, int NV, bool MULTI, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (BLOCK == 256 ? (NV <= 4 ? 3 : 2) : 1))
+    row_select_fast_kernel(void* __restrict__ W, int64_t R, int C, int64_t ld, const float* __restrict__ scaler_row, int k,
+                           int G, uint8_t* __restrict__ mask_bits, int64_t mask_ld,
+                           unsigned long long* __restrict__ n_zero) {
+  constexpr int NP = 4 * NV;  // packed pairs per lane
+  constexpr bool F32 = (DT == ECF_F32);
+  extern __shared__ __align__(16) float qtab[];
+  __shared__ RfShared sh;
+
+  const int tid = threadIdx.x;
+  const int cpad = NV * G * 8;
+  for (int c = tid; c < cpad; c += BLOCK) qtab[c] = c < C ? __fadd_rn(sqrtf(scaler_row[c]), 0.f) : 0.f;
+  __syncthreads();
+
+  const int group = tid / G;
+  const int gl = tid - group * G;
+  const int lane = tid & 31;
+  const int wig = gl >> 5;  // warp inside the group
+  const int rows_per_cta = BLOCK / G;
+  int parity = 0;
+  int zeros = 0;
+
+  for (int64_t row = (int64_t)blockIdx.x * rows_per_cta + group; row < R; row += (int64_t)gridDim.x * rows_per_cta) {
+    char* wrow = reinterpret_cast<char*>(W) + row * ld * DType<DT>::kBytes;
+    uint8_t* mask_row = mask_bits != nullptr ? mask_bits + row * mask_ld : nullptr;
+    uint32_t co[NP];
+    uint32_t raw[F32 ? 1 : NP];
+
+    // ---- load the row once, exact scores -> packed coarse keys ----------------------------------
+    if constexpr (!F32) {
+      uint4 v[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c0 = (i * G + gl) * 8;
+        v[i] = c0 < C ? ldg_v4(wrow + (int64_t)c0 * 2) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c0 = (i * G + gl) * 8;
+        raw[4 * i + 0] = v[i].x; raw[4 * i + 1] = v[i].y; raw[4 * i + 2] = v[i].z; raw[4 * i + 3] = v[i].w;
+        const float4 qa = *reinterpret_cast<const float4*>(qtab + c0), qb = *reinterpret_cast<const float4*>(qtab + c0 + 4);
+        const float q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float w0, w1;
+          unpack2<DT>(raw[4 * i + j], w0, w1);
+          co[4 * i + j] = c0 < C ? rf_coarse_pair(w0, w1, q[2 * j], q[2 * j + 1]) : rf_dup(kRfInf);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c0 = (i * G + gl) * 8;
+        uint4 a = make_uint4(0, 0, 0, 0), b = a;
+        if (c0 < C) {
+          a = ldg_v4(wrow + (int64_t)c0 * 4);
+          b = ldg_v4(wrow + (int64_t)c0 * 4 + 16);
+        }
+        const float4 qa = *reinterpret_cast<const float4*>(qtab + c0), qb = *reinterpret_cast<const float4*>(qtab + c0 + 4);
+        const uint32_t inf2 = rf_dup(kRfInf);
+        co[4 * i + 0] = c0 < C ? rf_coarse_pair(__uint_as_float(a.x), __uint_as_float(a.y), qa.x, qa.y) : inf2;
+        co[4 * i + 1] = c0 < C ? rf_coarse_pair(__uint_as_float(a.z), __uint_as_float(a.w), qa.z, qa.w) : inf2;
+        co[4 * i + 2] = c0 < C ? rf_coarse_pair(__uint_as_float(b.x), __uint_as_float(b.y), qb.x, qb.y) : inf2;
+        co[4 * i + 3] = c0 < C ? rf_coarse_pair(__uint_as_float(b.z), __uint_as_float(b.w), qb.z, qb.w) : inf2;
+      }
+      raw[0] = 0;
+    }
+
+    // ---- coarse bracket [lo, hi):  #(coarse < lo) < k <= #(coarse < hi) ----------------------------
+    uint32_t lo = 0, hi = 0;
+    int c_lo = 0, c_hi = 0;
+    if (k >= C) {
+      lo = hi = kRfInf;  // every real element is below the bracket
+    } else if (k > 0) {
+      if (gl == 0) sh.cand_n[group] = 0;
+      if constexpr (!MULTI) __syncwarp();
+      // seed: 32 samples (first element of vector 0 of the group's first warp), bitonic sort
+      const int ns = min(32, C >> 3);
+      if (wig == 0) {
+        uint32_t v = (gl * 8 < C) ? (co[0] & 0xffffu) : kRfInf;
+#pragma unroll
+        for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+          for (int j = kk >> 1; j > 0; j >>= 1) {
+            const uint32_t o = __shfl_xor_sync(0xffffffffu, v, j);
+            const bool up = (lane & kk) == 0, lower = (lane & j) == 0;
+            v = (up == lower) ? min(v, o) : max(v, o);
+          }
+        }
+        const int r = (int)(((int64_t)k * ns) / C);
+        const int il = r - 3, ih = r + 3;
+        const uint32_t vlo = __shfl_sync(0xffffffffu, v, il < 0 ? 0 : il);
+        const uint32_t vhi = __shfl_sync(0xffffffffu, v, ih > 31 ? 31 : ih);
+        lo = il >= 0 ? vlo : 0u;
+        hi = ih < ns ? vhi + 1u : kRfInf;
+        if constexpr (MULTI) {
+          if (lane == 0) { sh.seed[group][0] = lo; sh.seed[group][1] = hi; }
+        }
+      }
+      if constexpr (MULTI) {
+        named_bar_sync(1 + group, G);
+        lo = sh.seed[group][0];
+        hi = sh.seed[group][1];
+      }
+      {
+        const int cc = rf_gsum<MULTI>(rf_count2<NP>(co, lo, hi), G, group, wig, lane, sh, parity);
+        c_lo = cc & 0xffff;
+        c_hi = cc >> 16;
+      }
+      if (c_lo >= k) { hi = lo; c_hi = c_lo; lo = 0; c_lo = 0; }
+      else if (c_hi < k) { lo = hi; c_lo = c_hi; hi = kRfInf; c_hi = C; }
+      int stall = 0;
+      while (c_hi - c_lo > kRfBand && hi - lo > 1) {
+        const int n = c_hi - c_lo;
+        uint32_t p;
+        if (stall >= 2) {
+          p = (lo + hi) >> 1;
+          stall = 0;
+        } else {
+          const int dl = k - c_lo, dh = c_hi - k;
+          const float target = (float)dl + (dl >= dh ? -(float)(kRfBand / 3) : (float)(kRfBand / 3));
+          const float f = fminf(fmaxf(target / (float)n, 0.f), 1.f);
+          p = lo + (uint32_t)__float2int_rn((float)(hi - lo) * f);
+        }
+        p = min(max(p, lo + 1), hi - 1);
+        const int c = rf_gsum<MULTI>(rf_count1<NP>(co, p), G, group, wig, lane, sh, parity);
+        if (c < k) { lo = p; c_lo = c; } else { hi = p; c_hi = c; }
+        stall = (c_hi - c_lo) * 2 > n ? stall + 1 : 0;
+      }
+    }
+
+    // ---- coarse apply (everything below the bracket goes) + store; record this lane's bracket elements ----
+    unsigned long long bm = 0ull;
+    {
+      const __half2 pl = rf_h2(rf_dup(lo)), ph = rf_h2(rf_dup(hi));
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c0 = (i * G + gl) * 8;
+        uint32_t ml[4];
+        uint32_t any = 0, bacc = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int p = 4 * i + j;
+          ml[j] = __hlt2_mask(rf_h2(co[p]), pl);
+          const uint32_t mh = __hlt2_mask(rf_h2(co[p]), ph);
+          bacc |= (mh ^ ml[j]) & ((1u << (2 * j)) | (0x10000u << (2 * j + 1)));
+          any |= ml[j];
+        }
+        bm |= (unsigned long long)((bacc | (bacc >> 16)) & 0xffu) << (8 * i);
+        if (c0 >= C) continue;
+        if constexpr (!F32) {
+          uint32_t v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = raw[4 * i + j] & ~ml[j];
+          if (any) stg_v4(wrow + (int64_t)c0 * 2, make_uint4(v[0], v[1], v[2], v[3]));
+          if (n_zero != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) zeros += ((v[j] & 0x00007fffu) == 0 ? 1 : 0) + ((v[j] & 0x7fff0000u) == 0 ? 1 : 0);
+          }
+        } else {
+          if (any || n_zero != nullptr) {
+            uint4 a = ldg_v4(wrow + (int64_t)c0 * 4), b = ldg_v4(wrow + (int64_t)c0 * 4 + 16);
+            uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (ml[j] & 0x0000ffffu) v[2 * j] = 0;
+              if (ml[j] & 0xffff0000u) v[2 * j + 1] = 0;
+            }
+            if (any) {
+              stg_v4(wrow + (int64_t)c0 * 4, make_uint4(v[0], v[1], v[2], v[3]));
+              stg_v4(wrow + (int64_t)c0 * 4 + 16, make_uint4(v[4], v[5], v[6], v[7]));
+            }
+            if (n_zero != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) zeros += ((v[j] & 0x7fffffffu) == 0) ? 1 : 0;
+            }
+          }
+        }
+        if (mask_row != nullptr) {
+          uint32_t mb = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mb |= ((ml[j] & 1u) | ((ml[j] >> 15) & 2u)) << (2 * j);
+          mask_row[c0 >> 3] = (uint8_t)mb;
+        }
+      }
+    }
+
+    // ---- exact ranking of the bracket by (fp32 key, column) ----------------------------------------------
+    const int m = c_hi - c_lo, need = k - c_lo;  // bracket size, how many of it must go (1 <= need <= m when m > 0)
+    if (m > 0) {
+      unsigned long long thr = ~0ull;  // need == m: the whole bracket goes
+      if (need < m) {
+        if (m <= kRfCap) {
+          rf_walk<DT, 0>(bm, wrow, qtab, G, gl, 0, 0, 0ull, sh.cand[group], &sh.cand_n[group], nullptr);
+          rf_gsync<MULTI>(group, G);
+          for (int t = gl; t < m; t += G) {
+            const unsigned long long me = sh.cand[group][t];
+            int rank = 0;
+            for (int j = 0; j < m; ++j) rank += sh.cand[group][j] < me ? 1 : 0;
+            if (rank == need - 1) sh.thr[group] = me;
+          }
+          rf_gsync<MULTI>(group, G);
+          thr = sh.thr[group];
+        } else {
+          // heavy ties: the bracket is a single coarse value.  Bisect the fp32 key, then the column.
+          uint32_t L = lo << 16, H = (lo >= 0x7bffu) ? 0x80000000u : ((lo + 1u) << 16);
+          int cL = 0;
+          while (H - L > 1) {
+            const uint32_t pv = L + ((H - L) >> 1);
+            const int c = rf_gsum<MULTI>(rf_walk<DT, 1>(bm, wrow, qtab, G, gl, pv, 0, 0ull, nullptr, nullptr, nullptr), G, group, wig,
+                                         lane, sh, parity);
+            if (c < need) { L = pv; cL = c; } else { H = pv; }
+          }
+          const int need2 = need - cL;        // ties at key L that must go, lowest column first
+          uint32_t CL = 0, CH = (uint32_t)C;  // #(ties with col < CL) < need2 <= #(ties with col < CH)
+          while (CH - CL > 1) {
+            const uint32_t pc = (CL + CH) >> 1;
+            const int c = rf_gsum<MULTI>(rf_walk<DT, 2>(bm, wrow, qtab, G, gl, L, pc, 0ull, nullptr, nullptr, nullptr), G, group, wig,
+                                         lane, sh, parity);
+            if (c < need2) CL = pc; else CH = pc;
+          }
+          thr = ((unsigned long long)L << 32) | CL;
+        }
+      }
+      // scalar fix-up of this lane's own bracket elements (after its own vector stores: same-thread order)
+      zeros += rf_walk<DT, 3>(bm, wrow, qtab, G, gl, 0, 0, thr, nullptr, nullptr, mask_row);
+      // the next row reuses sh.cand / sh.thr / sh.seed: every lane of the group must be done with them
+      rf_gsync<MULTI>(group, G);
+    }
+  }
+  if (n_zero != nullptr) {
+    const int z = warp_sum(zeros);
+    if (lane == 0 && z) atomicAdd(n_zero, (unsigned long long)z);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+template <int DT, int NV, bool MULTI, int BLOCK>
+static int rf_launch(void* W, int64_t R, int C, int64_t ld, const float* s, int k, int G, uint8_t* mask, int64_t mask_ld,
+                     unsigned long long* nz, cudaStream_t stream) {
+  auto kern = row_select_fast_kernel<DT, NV, MULTI, BLOCK>;
+  const size_t smem = (size_t)NV * G * 8 * sizeof(float);
+  static size_t smem_opted = 0;  // largest dynamic size this instantiation has been opted in for
+  if (smem + sizeof(RfShared) > 48 * 1024 && smem > smem_opted) {
+    ECF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_opted = smem;
+  }
+  int occ = 0;
+  ECF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem));
+  if (occ < 1) occ = 1;
+  const int rows_per_cta = BLOCK / G;
+  const int64_t batches = (R + rows_per_cta - 1) / rows_per_cta;
+  const int64_t cap = (int64_t)sm_count() * occ;
+  const unsigned grid = (unsigned)(batches < cap ? batches : cap);
+  kern<<<grid, BLOCK, smem, stream>>>(W, R, C, ld, s, k, G, mask, mask_ld, nz);
+  ECF_CUDA_OK(cudaGetLastError());
+  return ECF_OK;
+}
+
+template <int DT, int NV>
+static int rf_dispatch_g(void* W, int64_t R, int C, int64_t ld, const float* s, int k, int G, uint8_t* mask, int64_t mask_ld,
+                         unsigned long long* nz, cudaStream_t stream) {
+  if (G == 32) return rf_launch<DT, NV, false, 256>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
+  if (G <= 256) return rf_launch<DT, NV, true, 256>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
+  return rf_launch<DT, NV, true, 512>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
+}
+
+// Requires: C % 8 == 0, 16-byte aligned rows, C <= 32768.
+template <int DT>
+static int run_row_select_fast(void* W, int64_t R, int64_t C, int64_t ld, const float* s, int64_t k, int nv_max, uint8_t* mask,
+                               int64_t mask_ld, unsigned long long* nz, cudaStream_t stream) {
+  const int64_t nvec = C / 8;
+  int G = 32;
+  while (G < 512 && (nvec + G - 1) / G > nv_max) G <<= 1;
+  int nv = (int)((nvec + G - 1) / G);
+  ECF_REQUIRE(nv <= 8, ECF_ERR_INVALID, "row_select: C=%lld exceeds the supported row length 32768", (long long)C);
+  if (nv == 7) nv = 8;
+  switch (nv) {
+#define ECF_CASE(N) \
+  case N: return rf_dispatch_g<DT, N>(W, R, (int)C, ld, s, (int)k, G, mask, mask_ld, nz, stream);
+    ECF_CASE(1) ECF_CASE(2) ECF_CASE(3) ECF_CASE(4) ECF_CASE(5) ECF_CASE(6) ECF_CASE(8)
+#undef ECF_CASE
+  }
+  set_error("row_select: unsupported vectors-per-lane %d", nv);
+  return ECF_ERR_INVALID;
+}
+
+}  // namespace ecf

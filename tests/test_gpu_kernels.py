@@ -145,6 +145,94 @@ def test_row_select_adversarial_ties(dt):
     assert np.array_equal(f32(Wd).view(np.uint32), Wref.view(np.uint32))
 
 
+@pytest.mark.parametrize("dt", ["fp16", "bf16", "fp32"])
+@pytest.mark.parametrize("C", [768, 2048, 5120, 11008])
+def test_row_select_heavy_ties_all_group_sizes(dt, C):
+    """thousands of equal scores per row (already-pruned weights, constant rows, dead channels): exercises the
+    in-register bisection on key and column for single-warp and multi-warp row groups."""
+    from ecoflap_b200 import ops
+
+    if dt == "fp32" and C > 8192:
+        pytest.skip("kept short: the fp32 long-row case is covered by test_row_select_bit_exact")
+    R = 24
+    W = synth_w(R, C, dt, seed=C + 17)
+    W[0] = 0                      # every score equal (zero)
+    W[1, ::2] = 0                 # half the row already pruned
+    W[2] = W[2, 5]                # constant row: ties decided by the norms only
+    W[3, : C // 2] = W[3, C // 2:]  # every score twice
+    W[4, 1::3] = 0
+    W[5] = 0
+    W[5, ::7] = 0.01              # few survivors
+    W[6, C // 3:] = 0             # zeros at the END of the row: the column tie-break must keep low indices pruned first
+    s = synth_norm(C, seed=C + 2)
+    s[C // 4: C // 4 + 40] = 0.0
+    s2 = np.full(C, 2.0, dtype=np.float32)
+    for norms in (s, s2):
+        for sparsity in (0.5, 0.3, 0.9, 0.02):
+            k = orc.row_k(C, sparsity)
+            Wd = W.clone().to(dev())
+            mb = ops.alloc_mask_bits(R, C, dev())
+            nz = torch.zeros(1, dtype=torch.int64, device=dev())
+            ops.wanda_row_select_apply(Wd, torch.from_numpy(norms).to(dev()), k, mask_bits=mb, n_zero=nz)
+            Wref, mref = orc.wanda_prune_rows(f32(W), norms, sparsity)
+            assert np.array_equal(f32(Wd).view(np.uint32), Wref.view(np.uint32)), (dt, C, sparsity)
+            assert np.array_equal(ops.unpack_mask_bits(mb, C).cpu().numpy(), mref)
+            assert int(nz.item()) == orc.count_zero(Wref)
+
+
+@pytest.mark.parametrize("dt", ["fp16", "bf16", "fp32"])
+def test_row_select_nonfinite_scores(dt):
+    """inf / NaN / huge scores sort last (NaN after inf), exactly like torch.sort; a NaN norm poisons its column."""
+    from ecoflap_b200 import ops
+
+    R, C = 8, 2048
+    W = synth_w(R, C, dt, seed=77)
+    W[0, 5] = float("inf")
+    W[0, 9] = float("nan")
+    W[1, :1500] = float("inf")     # k reaches into the inf ties
+    W[2, 100:1700] = float("nan")  # ... and into the NaN ties
+    W[3, ::2] = float("nan")
+    s = synth_norm(C, seed=5)
+    s[11] = 1e30
+    s[12] = float("inf")
+    s[13] = float("nan")
+    for sparsity in (0.5, 0.9):
+        k = orc.row_k(C, sparsity)
+        Wd = W.clone().to(dev())
+        mb = ops.alloc_mask_bits(R, C, dev())
+        ops.wanda_row_select_apply(Wd, torch.from_numpy(s).to(dev()), k, mask_bits=mb)
+        _, mref = orc.wanda_prune_rows(f32(W), s, sparsity)
+        assert np.array_equal(ops.unpack_mask_bits(mb, C).cpu().numpy(), mref), (dt, sparsity)
+        # raw storage bits: fp16/bf16 NaN payloads do not survive a float() round trip identically on CPU and GPU
+        it = torch.int32 if dt == "fp32" else torch.int16
+        got, orig = Wd.cpu().view(it).numpy(), W.view(it).numpy()
+        assert np.array_equal(got[~mref], orig[~mref])
+        assert not got[mref].any()
+
+
+@pytest.mark.parametrize("dt", ["fp16", "bf16"])
+def test_row_select_full_size_properties(dt):
+    """BASELINE.json full sizes (T5-XL wi / LLaMA-7B down_proj): exactly k zeros per row, kept weights untouched,
+    idempotent-compatible with the per-row threshold property max(pruned score) <= min(kept score)."""
+    from ecoflap_b200 import ops
+
+    for R, C in ((5120, 2048), (4096, 11008)):
+        W = synth_w(R, C, dt, seed=R + C)
+        s = torch.from_numpy(synth_norm(C, seed=1)).to(dev())
+        Wd = W.clone().to(dev())
+        k = C // 2
+        mb = ops.alloc_mask_bits(R, C, dev())
+        ops.wanda_row_select_apply(Wd, s, k, mask_bits=mb)
+        mask = ops.unpack_mask_bits(mb, C)
+        assert torch.equal(mask.sum(1), torch.full((R,), k, device=dev()))
+        W0 = W.to(dev())
+        assert torch.equal(Wd[~mask], W0[~mask]) and not Wd[mask].any()
+        score = W0.float().abs() * s.sqrt()[None, :]
+        hi_pruned = torch.where(mask, score, torch.full_like(score, -1.0)).max(1).values
+        lo_kept = torch.where(mask, torch.full_like(score, float("inf")), score).min(1).values
+        assert bool((hi_pruned <= lo_kept).all())
+
+
 def test_row_select_strided_weight():
     from ecoflap_b200 import ops
 

@@ -6,7 +6,12 @@ import torch
 from ecoflap_b200 import ops
 
 dev = torch.device("cuda", 0)
-PEAK = 6558.7
+PEAK = 6551.4
+ONLY = set(sys.argv[1:])  # e.g. `kernel_probe.py row_select layer_thresh`; empty = everything
+
+
+def want(k):
+    return not ONLY or k in ONLY
 
 
 def timeit(fn, reps=20, flush=None):
@@ -26,7 +31,7 @@ def timeit(fn, reps=20, flush=None):
 
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 out = []
-for (T, C, dt) in [(32896, 1408, torch.float16), (32896, 1408, torch.float32), (32896, 6144, torch.float16), (8192, 2048, torch.bfloat16),
+for (T, C, dt) in [] if not want('sqnorm') else [(2056, 1408, torch.float32), (2056, 6144, torch.float16), (512, 2048, torch.bfloat16), (32896, 1408, torch.float16), (32896, 1408, torch.float32), (32896, 6144, torch.float16), (8192, 2048, torch.bfloat16),
                    (8192, 5120, torch.bfloat16), (262144, 4096, torch.float16), (65536, 2048, torch.bfloat16)]:
     x = torch.randn(T, C, device=dev, dtype=dt)
     s = torch.zeros(C, device=dev)
@@ -35,8 +40,8 @@ for (T, C, dt) in [(32896, 1408, torch.float16), (32896, 1408, torch.float32), (
     out.append(dict(k="sqnorm", T=T, C=C, dt=str(dt), ms=ms, GBs=gb / ms * 1e3, frac=gb / ms * 1e3 / PEAK))
     print(out[-1], flush=True)
     del x
-for (R, C, dt) in [(2048, 2048, torch.bfloat16), (5120, 2048, torch.bfloat16), (2048, 5120, torch.bfloat16), (4096, 4096, torch.float16),
-                   (11008, 4096, torch.float16), (4096, 11008, torch.float16), (3072, 768, torch.float16)]:
+for (R, C, dt) in [] if not want('row_select') else [(2048, 2048, torch.bfloat16), (5120, 2048, torch.bfloat16), (2048, 5120, torch.bfloat16), (4096, 4096, torch.float16),
+                   (11008, 4096, torch.float16), (4096, 11008, torch.float16), (3072, 768, torch.float16), (3072, 768, torch.float32), (16384, 2048, torch.bfloat16)]:
     W0 = (torch.randn(R, C, device=dev) * 0.02).to(dt)
     s = torch.rand(C, device=dev) + 0.1
     W = W0.clone()
@@ -52,7 +57,7 @@ for (R, C, dt) in [(2048, 2048, torch.bfloat16), (5120, 2048, torch.bfloat16), (
     gb = (2 * R * C * W.element_size() + 4 * C) / 1e9
     out.append(dict(k="row_select", R=R, C=C, dt=str(dt), ms=ms, GBs=gb / ms * 1e3, frac=gb / ms * 1e3 / PEAK))
     print(out[-1], flush=True)
-for (R, C, dt) in [(4224, 1408, torch.float16), (6144, 1408, torch.float16), (1408, 6144, torch.float16), (3072, 768, torch.float32)]:
+for (R, C, dt) in [] if not want('layer_thresh') else [(4224, 1408, torch.float16), (6144, 1408, torch.float16), (1408, 6144, torch.float16), (3072, 768, torch.float32)]:
     W0 = (torch.randn(R, C, device=dev) * 0.02).to(dt)
     s = torch.rand(C, device=dev) + 0.1
     W = W0.clone()
@@ -65,6 +70,10 @@ for (R, C, dt) in [(4224, 1408, torch.float16), (6144, 1408, torch.float16), (14
     gb = (2 * R * C * W.element_size() + 4 * C) / 1e9
     out.append(dict(k="layer_thresh", R=R, C=C, dt=str(dt), ms=ms, GBs=gb / ms * 1e3, frac=gb / ms * 1e3 / PEAK))
     print(out[-1], flush=True)
+if not want('misc'):
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(out, open("gpurun_out/kernel_probe_%s.json" % os.environ.get("PROBE_TAG", "x"), "w"), indent=1)
+    sys.exit(0)
 ts_ = [(torch.randn(4096, 4096, device=dev) * 0.02).to(torch.bfloat16) for _ in range(64)]
 ms = timeit(lambda: ops.group_abs_reduce(ts_), flush=flush)
 gb = sum(t.numel() * 2 for t in ts_) / 1e9
