@@ -18,6 +18,7 @@ ERR_INVALID, ERR_WORKSPACE, ERR_CUDA, ERR_NO_DEVICE, ERR_RANGE = -1, -2, -3, -4,
 
 EXPORTED = (
     "ecf_version", "ecf_last_error", "ecf_device_sm_count", "ecf_workspace_bytes", "ecf_sqnorm_accum",
+    "ecf_sqnorm_batched_workspace_bytes", "ecf_sqnorm_accum_batched",
     "ecf_wanda_row_select_apply", "ecf_wanda_layer_thresh_apply", "ecf_group_reduce_chunk_elems",
     "ecf_group_abs_reduce", "ecf_zo_perturb", "ecf_count_zero", "ecf_hessian_accum", "ecf_obs_prune",
 )
@@ -34,6 +35,15 @@ class TensorDesc(C.Structure):
                 ("chunk_begin", C.c_int64)]
 
 
+class SqnormDesc(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("scaler_row", C.c_void_p), ("T", C.c_int64), ("C", C.c_int64), ("ld", C.c_int64),
+                ("dtype", C.c_int32), ("rescale", C.c_float), ("inv_n", C.c_float)]
+
+
+SQNORM_MAX_BATCH = 256
+SQNORM_MAX_GROUPS = 32
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -48,6 +58,8 @@ def _load():
         "ecf_device_sm_count": (i32, []),
         "ecf_workspace_bytes": (sz, [i32, i64, i64]),
         "ecf_sqnorm_accum": (i32, [vp, i32, i64, i64, i64, vp, f32, f32, vp, sz, vp]),
+        "ecf_sqnorm_batched_workspace_bytes": (sz, [C.POINTER(SqnormDesc), i32]),
+        "ecf_sqnorm_accum_batched": (i32, [C.POINTER(SqnormDesc), i32, vp, sz, vp]),
         "ecf_wanda_row_select_apply": (i32, [vp, i32, i64, i64, i64, vp, i64, vp, i64, vp, vp, sz, vp]),
         "ecf_wanda_layer_thresh_apply": (i32, [vp, i32, i64, i64, i64, vp, i64, vp, vp, i64, vp, vp, sz, vp]),
         "ecf_group_reduce_chunk_elems": (i64, []),

@@ -33,10 +33,47 @@ def _flatten_tokens(layer, inp):
     return b, inp
 
 
+class NormBatch:
+    """Collects ``WrappedGPT.add_batch`` calls and issues them as ONE kernel launch (``ecf_sqnorm_accum_batched``).
+    The reference fires one hook per Linear per calibration batch (wanda_pruner.py:238-253); at BLIP-2 sizes a hook
+    input is 1-25 MB, i.e. a few microseconds of HBM time, so per-hook launches are pure launch latency.  A batch may
+    span the Linears of a block AND successive calibration batches (the kernel applies repeated updates of one
+    accumulator in call order), so a block's whole calibration sweep becomes one launch of hundreds of MB.
+
+    The hook inputs are only referenced, not copied, until ``flush()``; ``max_bytes`` bounds what is kept alive
+    (an automatic flush happens when it is exceeded).  A block that overwrote a Linear's input in place between the
+    hook and the flush would corrupt the norms, so the tensor version counters are checked and a mismatch raises
+    (use ``WrappedGPT(...)`` without a batch for such a model)."""
+
+    def __init__(self, max_bytes: int = 4 << 30):
+        self._items = []   # (x, scaler_row, rescale, inv_n, version)
+        self._bytes = 0
+        self.max_bytes = int(max_bytes)
+
+    def add(self, x, scaler_row, rescale, inv_n):
+        self._items.append((x, scaler_row, rescale, inv_n, x._version))
+        self._bytes += x.numel() * x.element_size()
+        if self._bytes > self.max_bytes:
+            self.flush()
+
+    def flush(self):
+        if not self._items:
+            return
+        for x, _, _, _, version in self._items:
+            if x._version != version:
+                raise RuntimeError("a hooked Linear input was modified in place before the batched norm launch; "
+                                   "construct WrappedGPT without a NormBatch for this model")
+        items, self._items, self._bytes = self._items, [], 0
+        ops.sqnorm_accum_batched([it[:4] for it in items])
+
+    def __len__(self):
+        return len(self._items)
+
+
 class WrappedGPT:
     """Running mean over samples of the per-input-channel sum of squared activations."""
 
-    def __init__(self, layer, layer_id=0, layer_name="none"):
+    def __init__(self, layer, layer_id=0, layer_name="none", batch: "NormBatch | None" = None):
         self.layer = layer
         self.dev = self.layer.weight.device
         self.rows = layer.weight.data.shape[0]
@@ -45,12 +82,16 @@ class WrappedGPT:
         self.nsamples = 0
         self.layer_id = layer_id
         self.layer_name = layer_name
+        self.batch = batch  # optional NormBatch: the launch is deferred to batch.flush()
 
     def add_batch(self, inp, out=None):
         b, x = _flatten_tokens(self.layer, inp)
         n = self.nsamples + b
         # scaler_row = scaler_row * n_old/n + colsum(x^2) / n   -- one fused kernel, X read once
-        ops.sqnorm_accum(x, self.scaler_row, self.nsamples / n, 1.0 / n)
+        if self.batch is not None:
+            self.batch.add(x, self.scaler_row, self.nsamples / n, 1.0 / n)
+        else:
+            ops.sqnorm_accum(x, self.scaler_row, self.nsamples / n, 1.0 / n)
         self.nsamples = n
 
 
@@ -143,4 +184,4 @@ class SparseGPT:
         torch.cuda.empty_cache()
 
 
-__all__ = ["WrappedGPT", "SparseGPT", "math"]
+__all__ = ["NormBatch", "WrappedGPT", "SparseGPT", "math"]

@@ -307,11 +307,12 @@ static int run_row_select(void* W, int64_t R, int64_t C, int64_t ld, const float
   return dispatch_nv<DT, false>(nv, W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
 }
 
-int row_select_fast_f16(void*, int64_t, int64_t, int64_t, const float*, int64_t, int, uint8_t*, int64_t, unsigned long long*, cudaStream_t);
-int row_select_fast_bf16(void*, int64_t, int64_t, int64_t, const float*, int64_t, int, uint8_t*, int64_t, unsigned long long*, cudaStream_t);
-int row_select_fast_f32(void*, int64_t, int64_t, int64_t, const float*, int64_t, int, uint8_t*, int64_t, unsigned long long*, cudaStream_t);
+int row_select_fast_f16(void*, int64_t, int64_t, int64_t, const float*, int64_t, int, bool, uint8_t*, int64_t, unsigned long long*, cudaStream_t);
+int row_select_fast_bf16(void*, int64_t, int64_t, int64_t, const float*, int64_t, int, bool, uint8_t*, int64_t, unsigned long long*, cudaStream_t);
+int row_select_fast_f32(void*, int64_t, int64_t, int64_t, const float*, int64_t, int, bool, uint8_t*, int64_t, unsigned long long*, cudaStream_t);
 
 // tuning / A-B switches (read once): ECF_RS_NVMAX = vectors per lane cap of the fast kernel (1..8),
+// ECF_RS_KEEP=0 makes 16-bit rows with > 4 vectors per lane re-read the weights in the apply pass (fewer registers),
 // ECF_RS_GENERIC=1 forces the generic kernel.
 static int rs_env(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -339,13 +340,14 @@ extern "C" int ecf_wanda_row_select_apply(void* W, int w_dtype, int64_t R, int64
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   static const int nv_max = [] { int v = rs_env("ECF_RS_NVMAX", 8); return v < 1 ? 1 : (v > 8 ? 8 : v); }();
   static const bool force_generic = rs_env("ECF_RS_GENERIC", 0) != 0;
+  static const bool keep = rs_env("ECF_RS_KEEP", 0) != 0;
   const int vec = w_dtype == ECF_F32 ? 4 : 8;
   const bool aligned = (C % 8 == 0) && (ld % vec == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
   if (aligned && !force_generic && C <= 32768 && w_dtype >= 0 && w_dtype <= 2) {
     switch (w_dtype) {
-      case ECF_F32: return row_select_fast_f32(W, R, C, ld, scaler_row, k_per_row, nv_max, mask_bits, mask_ld, n_zero, s);
-      case ECF_F16: return row_select_fast_f16(W, R, C, ld, scaler_row, k_per_row, nv_max, mask_bits, mask_ld, n_zero, s);
-      case ECF_BF16: return row_select_fast_bf16(W, R, C, ld, scaler_row, k_per_row, nv_max, mask_bits, mask_ld, n_zero, s);
+      case ECF_F32: return row_select_fast_f32(W, R, C, ld, scaler_row, k_per_row, nv_max, keep, mask_bits, mask_ld, n_zero, s);
+      case ECF_F16: return row_select_fast_f16(W, R, C, ld, scaler_row, k_per_row, nv_max, keep, mask_bits, mask_ld, n_zero, s);
+      case ECF_BF16: return row_select_fast_bf16(W, R, C, ld, scaler_row, k_per_row, nv_max, keep, mask_bits, mask_ld, n_zero, s);
     }
   }
   switch (w_dtype) {

@@ -69,13 +69,13 @@ __device__ __forceinline__ int rf_gsum(int v, int G, int group, int wig, int lan
 template <int NP>
 __device__ __forceinline__ int rf_count1(const uint32_t (&co)[NP], uint32_t pivot) {
   const __half2 pv = rf_h2(rf_dup(pivot));
-  __half2 a0 = rf_h2(0u), a1 = rf_h2(0u);
+  __half2 a[4] = {rf_h2(0u), rf_h2(0u), rf_h2(0u), rf_h2(0u)};  // NP is a multiple of 4: four independent chains
 #pragma unroll
-  for (int p = 0; p < NP; p += 2) {
-    a0 = __hadd2(a0, __hlt2(rf_h2(co[p]), pv));
-    a1 = __hadd2(a1, __hlt2(rf_h2(co[p + 1]), pv));
+  for (int p = 0; p < NP; p += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = __hadd2(a[u], __hlt2(rf_h2(co[p + u]), pv));
   }
-  const float2 f = __half22float2(__hadd2(a0, a1));
+  const float2 f = __half22float2(__hadd2(__hadd2(a[0], a[1]), __hadd2(a[2], a[3])));
   return (int)(f.x + f.y);
 }
 
@@ -95,23 +95,24 @@ __device__ __forceinline__ int rf_count2(const uint32_t (&co)[NP], uint32_t lo, 
 }
 
 __device__ __forceinline__ uint32_t rf_coarse_pair(float w0, float w1, float q0, float q1) {
-  const uint32_t b0 = min(__float_as_uint(__fmul_rn(fabsf(w0), q0)), 0x7bffffffu);
-  const uint32_t b1 = min(__float_as_uint(__fmul_rn(fabsf(w1), q1)), 0x7bffffffu);
-  return __byte_perm(b0, b1, 0x7632);  // (b1 >> 16) << 16 | (b0 >> 16)
+  const uint32_t b0 = __float_as_uint(__fmul_rn(fabsf(w0), q0)), b1 = __float_as_uint(__fmul_rn(fabsf(w1), q1));
+  // upper halves of both scores, each clamped to the largest finite fp16 pattern (one VIMNMX.U16x2)
+  return __vminu2(__byte_perm(b0, b1, 0x7632), 0x7bff7bffu);
 }
 
 // Lane-local walk over the bracket elements recorded in `bm` (bit e = element e of this lane: vector e >> 3,
-// slot e & 7).  The weight is re-read from global memory (an L1/L2 hit: this lane has just streamed the row), so
-// no register array is indexed dynamically and the code stays small.
+// slot e & 7; `ebase` = 0 for the low word, 32 for the high word).  The weight is re-read from global memory (an
+// L1/L2 hit: this lane has just streamed the row), so no register array is indexed dynamically and the code stays
+// small.
 //   MODE 0: append (key, column) to the shared candidate list
 //   MODE 1: count keys < a                    MODE 2: count keys == a with column < b
 //   MODE 3: zero the element when (key, column) <= thr; patch the packed mask; count new zeros
 template <int DT, int MODE>
-__device__ __forceinline__ int rf_walk(unsigned long long bm, char* wrow, const float* qtab, int G, int gl, uint32_t a, uint32_t b,
+__device__ __forceinline__ int rf_walk(uint32_t bm, int ebase, char* wrow, const float* qtab, int G, int gl, uint32_t a, uint32_t b,
                                        unsigned long long thr, unsigned long long* cand, int* cand_n, uint8_t* mask_row) {
   int c = 0;
   while (bm) {
-    const int e = __ffsll((long long)bm) - 1;
+    const int e = ebase + __ffs((int)bm) - 1;
     bm &= bm - 1;
     const uint32_t col = (uint32_t)(((e >> 3) * G + gl) * 8 + (e & 7));
     const float w = load_elem<DT>(wrow, col);
@@ -133,13 +134,28 @@ __device__ __forceinline__ int rf_walk(unsigned long long bm, char* wrow, const 
   return c;
 }
 
-template <int DT, int NV, bool MULTI, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK == 256 ? (NV <= 4 ? 3 : 2) : 1))
+template <int DT, int MODE>
+__device__ __forceinline__ int rf_walk2(uint32_t bm0, uint32_t bm1, char* wrow, const float* qtab, int G, int gl, uint32_t a,
+                                        uint32_t b, unsigned long long thr, unsigned long long* cand, int* cand_n,
+                                        uint8_t* mask_row) {
+  return rf_walk<DT, MODE>(bm0, 0, wrow, qtab, G, gl, a, b, thr, cand, cand_n, mask_row) +
+         rf_walk<DT, MODE>(bm1, 32, wrow, qtab, G, gl, a, b, thr, cand, cand_n, mask_row);
+}
+
+// byte-granular OR into the packed mask from a lane that does not own the byte
+__device__ __forceinline__ void rf_mask_or(uint8_t* mask_row, uint32_t col) {
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(mask_row + (col >> 3));
+  atomicOr(reinterpret_cast<unsigned*>(addr & ~uintptr_t(3)), 1u << ((addr & 3) * 8 + (col & 7)));
+}
+
+template <int DT, int NV, bool MULTI, int BLOCK, bool KEEP>
+__global__ void __launch_bounds__(BLOCK, (BLOCK == 256 ? ((NV <= 4 || !KEEP) ? 3 : 2) : 1))
     row_select_fast_kernel(void* __restrict__ W, int64_t R, int C, int64_t ld, const float* __restrict__ scaler_row, int k,
                            int G, uint8_t* __restrict__ mask_bits, int64_t mask_ld,
                            unsigned long long* __restrict__ n_zero) {
   constexpr int NP = 4 * NV;  // packed pairs per lane
   constexpr bool F32 = (DT == ECF_F32);
+  constexpr bool REREAD = F32 || !KEEP;  // weights are not kept in registers: the apply pass re-reads the row (L2 hit)
   extern __shared__ __align__(16) float qtab[];
   __shared__ RfShared sh;
 
@@ -160,7 +176,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 256 ? (NV <= 4 ? 3 : 2) : 1))
     char* wrow = reinterpret_cast<char*>(W) + row * ld * DType<DT>::kBytes;
     uint8_t* mask_row = mask_bits != nullptr ? mask_bits + row * mask_ld : nullptr;
     uint32_t co[NP];
-    uint32_t raw[F32 ? 1 : NP];
+    uint32_t raw[REREAD ? 1 : NP];
 
     // ---- load the row once, exact scores -> packed coarse keys ----------------------------------
     if constexpr (!F32) {
@@ -173,13 +189,14 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 256 ? (NV <= 4 ? 3 : 2) : 1))
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int c0 = (i * G + gl) * 8;
-        raw[4 * i + 0] = v[i].x; raw[4 * i + 1] = v[i].y; raw[4 * i + 2] = v[i].z; raw[4 * i + 3] = v[i].w;
+        const uint32_t rv[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+        if constexpr (!REREAD) { raw[4 * i + 0] = rv[0]; raw[4 * i + 1] = rv[1]; raw[4 * i + 2] = rv[2]; raw[4 * i + 3] = rv[3]; }
         const float4 qa = *reinterpret_cast<const float4*>(qtab + c0), qb = *reinterpret_cast<const float4*>(qtab + c0 + 4);
         const float q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float w0, w1;
-          unpack2<DT>(raw[4 * i + j], w0, w1);
+          unpack2<DT>(rv[j], w0, w1);
           co[4 * i + j] = c0 < C ? rf_coarse_pair(w0, w1, q[2 * j], q[2 * j + 1]) : rf_dup(kRfInf);
         }
       }
@@ -199,8 +216,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 256 ? (NV <= 4 ? 3 : 2) : 1))
         co[4 * i + 2] = c0 < C ? rf_coarse_pair(__uint_as_float(b.x), __uint_as_float(b.y), qb.x, qb.y) : inf2;
         co[4 * i + 3] = c0 < C ? rf_coarse_pair(__uint_as_float(b.z), __uint_as_float(b.w), qb.z, qb.w) : inf2;
       }
-      raw[0] = 0;
     }
+    if constexpr (REREAD) raw[0] = 0;
 
     // ---- coarse bracket [lo, hi):  #(coarse < lo) < k <= #(coarse < hi) ----------------------------
     uint32_t lo = 0, hi = 0;
@@ -255,7 +272,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 256 ? (NV <= 4 ? 3 : 2) : 1))
         } else {
           const int dl = k - c_lo, dh = c_hi - k;
           const float target = (float)dl + (dl >= dh ? -(float)(kRfBand / 3) : (float)(kRfBand / 3));
-          const float f = fminf(fmaxf(target / (float)n, 0.f), 1.f);
+          const float f = __saturatef(__fdividef(target, (float)n));
           p = lo + (uint32_t)__float2int_rn((float)(hi - lo) * f);
         }
         p = min(max(p, lo + 1), hi - 1);
@@ -266,34 +283,40 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 256 ? (NV <= 4 ? 3 : 2) : 1))
     }
 
     // ---- coarse apply (everything below the bracket goes) + store; record this lane's bracket elements ----
-    unsigned long long bm = 0ull;
+    uint32_t bm0 = 0, bm1 = 0;  // bit e: element e (vectors 0-3) / 32 + e (vectors 4-7) of this lane lies in the bracket
     {
       const __half2 pl = rf_h2(rf_dup(lo)), ph = rf_h2(rf_dup(hi));
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int c0 = (i * G + gl) * 8;
         uint32_t ml[4];
-        uint32_t any = 0, bacc = 0;
+        uint32_t bacc = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int p = 4 * i + j;
           ml[j] = __hlt2_mask(rf_h2(co[p]), pl);
           const uint32_t mh = __hlt2_mask(rf_h2(co[p]), ph);
           bacc |= (mh ^ ml[j]) & ((1u << (2 * j)) | (0x10000u << (2 * j + 1)));
-          any |= ml[j];
         }
-        bm |= (unsigned long long)((bacc | (bacc >> 16)) & 0xffu) << (8 * i);
+        if (i < 4) bm0 |= ((bacc | (bacc >> 16)) & 0xffu) << (8 * (i & 3));
+        else bm1 |= ((bacc | (bacc >> 16)) & 0xffu) << (8 * (i & 3));
         if (c0 >= C) continue;
         if constexpr (!F32) {
           uint32_t v[4];
+          if constexpr (REREAD) {
+            const uint4 a = ldg_v4(wrow + (int64_t)c0 * 2);
+            v[0] = a.x & ~ml[0]; v[1] = a.y & ~ml[1]; v[2] = a.z & ~ml[2]; v[3] = a.w & ~ml[3];
+          } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = raw[4 * i + j] & ~ml[j];
-          if (any) stg_v4(wrow + (int64_t)c0 * 2, make_uint4(v[0], v[1], v[2], v[3]));
+            for (int j = 0; j < 4; ++j) v[j] = raw[4 * i + j] & ~ml[j];
+          }
+          stg_v4(wrow + (int64_t)c0 * 2, make_uint4(v[0], v[1], v[2], v[3]));
           if (n_zero != nullptr) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) zeros += ((v[j] & 0x00007fffu) == 0 ? 1 : 0) + ((v[j] & 0x7fff0000u) == 0 ? 1 : 0);
           }
         } else {
+          const uint32_t any = ml[0] | ml[1] | ml[2] | ml[3];
           if (any || n_zero != nullptr) {
             uint4 a = ldg_v4(wrow + (int64_t)c0 * 4), b = ldg_v4(wrow + (int64_t)c0 * 4 + 16);
             uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -324,42 +347,57 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 256 ? (NV <= 4 ? 3 : 2) : 1))
     // ---- exact ranking of the bracket by (fp32 key, column) ----------------------------------------------
     const int m = c_hi - c_lo, need = k - c_lo;  // bracket size, how many of it must go (1 <= need <= m when m > 0)
     if (m > 0) {
-      unsigned long long thr = ~0ull;  // need == m: the whole bracket goes
-      if (need < m) {
-        if (m <= kRfCap) {
-          rf_walk<DT, 0>(bm, wrow, qtab, G, gl, 0, 0, 0ull, sh.cand[group], &sh.cand_n[group], nullptr);
-          rf_gsync<MULTI>(group, G);
+      if (m <= kRfCap) {
+        // gather the bracket into shared memory (lane-local walk), rank, then one lane per candidate patches it.
+        // The barrier after the gather also orders every lane's vector stores before the scalar patches.
+        rf_walk2<DT, 0>(bm0, bm1, wrow, qtab, G, gl, 0, 0, 0ull, sh.cand[group], &sh.cand_n[group], nullptr);
+        rf_gsync<MULTI>(group, G);
+        unsigned long long thr = ~0ull;  // need == m: the whole bracket goes
+        if (need < m) {
           for (int t = gl; t < m; t += G) {
             const unsigned long long me = sh.cand[group][t];
             int rank = 0;
+#pragma unroll 4
             for (int j = 0; j < m; ++j) rank += sh.cand[group][j] < me ? 1 : 0;
             if (rank == need - 1) sh.thr[group] = me;
           }
           rf_gsync<MULTI>(group, G);
           thr = sh.thr[group];
-        } else {
-          // heavy ties: the bracket is a single coarse value.  Bisect the fp32 key, then the column.
+        }
+        for (int t = gl; t < m; t += G) {
+          const unsigned long long me = sh.cand[group][t];
+          if (me <= thr) {
+            const uint32_t col = (uint32_t)me;
+            if (n_zero != nullptr) zeros += load_elem<DT>(wrow, col) != 0.f ? 1 : 0;
+            store_zero<DT>(wrow, col);
+            if (mask_row != nullptr) rf_mask_or(mask_row, col);
+          }
+        }
+      } else {
+        // heavy ties: the bracket is a single coarse value.  Bisect the fp32 key, then the column.
+        unsigned long long thr = ~0ull;
+        if (need < m) {
           uint32_t L = lo << 16, H = (lo >= 0x7bffu) ? 0x80000000u : ((lo + 1u) << 16);
           int cL = 0;
           while (H - L > 1) {
             const uint32_t pv = L + ((H - L) >> 1);
-            const int c = rf_gsum<MULTI>(rf_walk<DT, 1>(bm, wrow, qtab, G, gl, pv, 0, 0ull, nullptr, nullptr, nullptr), G, group, wig,
-                                         lane, sh, parity);
+            const int c = rf_gsum<MULTI>(rf_walk2<DT, 1>(bm0, bm1, wrow, qtab, G, gl, pv, 0, 0ull, nullptr, nullptr, nullptr), G,
+                                         group, wig, lane, sh, parity);
             if (c < need) { L = pv; cL = c; } else { H = pv; }
           }
           const int need2 = need - cL;        // ties at key L that must go, lowest column first
           uint32_t CL = 0, CH = (uint32_t)C;  // #(ties with col < CL) < need2 <= #(ties with col < CH)
           while (CH - CL > 1) {
             const uint32_t pc = (CL + CH) >> 1;
-            const int c = rf_gsum<MULTI>(rf_walk<DT, 2>(bm, wrow, qtab, G, gl, L, pc, 0ull, nullptr, nullptr, nullptr), G, group, wig,
-                                         lane, sh, parity);
+            const int c = rf_gsum<MULTI>(rf_walk2<DT, 2>(bm0, bm1, wrow, qtab, G, gl, L, pc, 0ull, nullptr, nullptr, nullptr), G,
+                                         group, wig, lane, sh, parity);
             if (c < need2) CL = pc; else CH = pc;
           }
           thr = ((unsigned long long)L << 32) | CL;
         }
+        // scalar patch of this lane's own bracket elements (after its own vector stores: same-thread order)
+        zeros += rf_walk2<DT, 3>(bm0, bm1, wrow, qtab, G, gl, 0, 0, thr, nullptr, nullptr, mask_row);
       }
-      // scalar fix-up of this lane's own bracket elements (after its own vector stores: same-thread order)
-      zeros += rf_walk<DT, 3>(bm, wrow, qtab, G, gl, 0, 0, thr, nullptr, nullptr, mask_row);
       // the next row reuses sh.cand / sh.thr / sh.seed: every lane of the group must be done with them
       rf_gsync<MULTI>(group, G);
     }
@@ -371,10 +409,10 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 256 ? (NV <= 4 ? 3 : 2) : 1))
 }
 
 // ---------------------------------------------------------------------------------------------- host
-template <int DT, int NV, bool MULTI, int BLOCK>
+template <int DT, int NV, bool MULTI, int BLOCK, bool KEEP>
 static int rf_launch(void* W, int64_t R, int C, int64_t ld, const float* s, int k, int G, uint8_t* mask, int64_t mask_ld,
                      unsigned long long* nz, cudaStream_t stream) {
-  auto kern = row_select_fast_kernel<DT, NV, MULTI, BLOCK>;
+  auto kern = row_select_fast_kernel<DT, NV, MULTI, BLOCK, KEEP>;
   const size_t smem = (size_t)NV * G * 8 * sizeof(float);
   static size_t smem_opted = 0;  // largest dynamic size this instantiation has been opted in for
   if (smem + sizeof(RfShared) > 48 * 1024 && smem > smem_opted) {
@@ -394,16 +432,28 @@ static int rf_launch(void* W, int64_t R, int C, int64_t ld, const float* s, int 
 }
 
 template <int DT, int NV>
-static int rf_dispatch_g(void* W, int64_t R, int C, int64_t ld, const float* s, int k, int G, uint8_t* mask, int64_t mask_ld,
-                         unsigned long long* nz, cudaStream_t stream) {
-  if (G == 32) return rf_launch<DT, NV, false, 256>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
-  if (G <= 256) return rf_launch<DT, NV, true, 256>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
-  return rf_launch<DT, NV, true, 512>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
+static int rf_dispatch_g(void* W, int64_t R, int C, int64_t ld, const float* s, int k, int G, bool keep, uint8_t* mask,
+                         int64_t mask_ld, unsigned long long* nz, cudaStream_t stream) {
+  // KEEP only changes code for 16-bit weights with more than 4 vectors per lane (fp32 always re-reads)
+  if constexpr (DT != ECF_F32 && NV > 4) {
+    if (keep) {
+      if (G == 32) return rf_launch<DT, NV, false, 256, true>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
+      if (G <= 256) return rf_launch<DT, NV, true, 256, true>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
+      return rf_launch<DT, NV, true, 512, true>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
+    }
+    if (G == 32) return rf_launch<DT, NV, false, 256, false>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
+    if (G <= 256) return rf_launch<DT, NV, true, 256, false>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
+    return rf_launch<DT, NV, true, 512, false>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
+  } else {
+    if (G == 32) return rf_launch<DT, NV, false, 256, true>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
+    if (G <= 256) return rf_launch<DT, NV, true, 256, true>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
+    return rf_launch<DT, NV, true, 512, true>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
+  }
 }
 
 // Requires: C % 8 == 0, 16-byte aligned rows, C <= 32768.
 template <int DT>
-static int run_row_select_fast(void* W, int64_t R, int64_t C, int64_t ld, const float* s, int64_t k, int nv_max, uint8_t* mask,
+static int run_row_select_fast(void* W, int64_t R, int64_t C, int64_t ld, const float* s, int64_t k, int nv_max, bool keep, uint8_t* mask,
                                int64_t mask_ld, unsigned long long* nz, cudaStream_t stream) {
   const int64_t nvec = C / 8;
   int G = 32;
@@ -413,7 +463,7 @@ static int run_row_select_fast(void* W, int64_t R, int64_t C, int64_t ld, const 
   if (nv == 7) nv = 8;
   switch (nv) {
 #define ECF_CASE(N) \
-  case N: return rf_dispatch_g<DT, N>(W, R, (int)C, ld, s, (int)k, G, mask, mask_ld, nz, stream);
+  case N: return rf_dispatch_g<DT, N>(W, R, (int)C, ld, s, (int)k, G, keep, mask, mask_ld, nz, stream);
     ECF_CASE(1) ECF_CASE(2) ECF_CASE(3) ECF_CASE(4) ECF_CASE(5) ECF_CASE(6) ECF_CASE(8)
 #undef ECF_CASE
   }

@@ -74,6 +74,39 @@ def sqnorm_accum(x: torch.Tensor, scaler_row: torch.Tensor, rescale: float, inv_
                                float(inv_n), ws.data_ptr(), ws.numel(), _stream(x)))
 
 
+def sqnorm_accum_batched(items) -> None:
+    """One launch for a list of ``(x, scaler_row, rescale, inv_n)`` hook calls (A1, batched).  ``x`` tensors may be
+    shared between items (q/k/v see the same input); items may also repeat a ``scaler_row`` (successive calibration
+    batches of one Linear), in which case they are applied in list order.  Lists beyond the ABI's limits (256 calls /
+    32 accumulators per launch) are issued as several launches, still in order."""
+    items = list(items)
+    keep = []  # contiguous copies must outlive the launch call
+    i = 0
+    while i < len(items):
+        rows, j = set(), i
+        while j < len(items) and j - i < _abi.SQNORM_MAX_BATCH:
+            ptr = items[j][1].data_ptr()
+            if ptr not in rows and len(rows) == _abi.SQNORM_MAX_GROUPS:
+                break
+            rows.add(ptr)
+            j += 1
+        chunk = items[i:j]
+        i = j
+        descs = (_abi.SqnormDesc * len(chunk))()
+        for d, (x, scaler_row, rescale, inv_n) in zip(descs, chunk):
+            _require_cuda(x, scaler_row)
+            assert scaler_row.dtype == torch.float32 and scaler_row.is_contiguous()
+            x2, T, C, ld = _as_2d(x)
+            assert scaler_row.numel() == C
+            keep.append(x2)
+            d.x, d.scaler_row, d.T, d.C, d.ld = x2.data_ptr(), scaler_row.data_ptr(), T, C, ld
+            d.dtype, d.rescale, d.inv_n = dtype_code(x2), float(rescale), float(inv_n)
+        dev = chunk[0][0].device
+        need = lib.ecf_sqnorm_batched_workspace_bytes(descs, len(chunk))
+        ws = _ws.get(dev, need, "sqnorm")
+        check(lib.ecf_sqnorm_accum_batched(descs, len(chunk), ws.data_ptr(), ws.numel(), _stream(chunk[0][0])))
+
+
 def _weight_2d(W: torch.Tensor):
     assert W.dim() == 2 and W.stride(1) == 1, "weight must be a row-major 2-D tensor"
     return W.shape[0], W.shape[1], (W.stride(0) if W.shape[0] > 1 else W.shape[1])

@@ -14,6 +14,7 @@ is done by the CUDA kernels behind ``WrappedGPT`` / ``SparseGPT`` / ``ops``.
 from __future__ import annotations
 
 import contextlib
+import os
 from dataclasses import dataclass, field
 from typing import Callable, Optional, Sequence
 
@@ -21,7 +22,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..accumulators import SparseGPT, WrappedGPT
+from ..accumulators import NormBatch, SparseGPT, WrappedGPT
 
 
 def get_module_recursive(base, module_to_process):
@@ -164,7 +165,12 @@ def sweep_blocks(pruner, model, dataloader, device, spec: SweepSpec, model_prefi
         layer = layers[i]
         restore = spec.block_adapter(layer, device) if spec.block_adapter is not None else None
         subset = find_layers(layer)
-        wrapped = {name: acc_cls(subset[name]) for name in subset}
+        # Wanda: the hook calls of the block's calibration sweep are deferred and become one batched norm launch
+        norm_batch = NormBatch() if (method == "wanda" and os.environ.get("ECF_NORM_BATCH", "1") != "0") else None
+        if method == "wanda":
+            wrapped = {name: WrappedGPT(subset[name], batch=norm_batch) for name in subset}
+        else:
+            wrapped = {name: acc_cls(subset[name]) for name in subset}
 
         def make_hook(name):
             permute = restore is not None and not name.startswith("hacky")
@@ -183,6 +189,8 @@ def sweep_blocks(pruner, model, dataloader, device, spec: SweepSpec, model_prefi
                 with torch.no_grad():
                     with autocast():
                         outs[j] = _run_block(layer, inps[j], caches[j], spec)
+            if norm_batch is not None:  # one launch for the whole calibration sweep of this block
+                norm_batch.flush()
         finally:
             for h in handles:
                 h.remove()

@@ -16,6 +16,7 @@ class LinearSpec:
     x_dtype: str       # dtype of the hook input
     tokens: int        # tokens per calibration batch fed to this Linear (batch * seq)
     select: str        # "row" | "layer"
+    src: str = ""      # name of the hook-input tensor inside the block: Linears with the same src see the SAME tensor
 
 
 @dataclass(frozen=True)
@@ -28,10 +29,10 @@ def vit_g_block(i, batch=8, tokens=257, prefix="visual_encoder.blocks"):
     T = batch * tokens
     # LayerNorm outputs reach qkv / fc1 as fp32 under autocast, attention/GELU outputs as fp16
     return BlockSpec(f"{prefix}.{i}", (
-        LinearSpec("attn.qkv", 4224, 1408, "fp16", "fp32", T, "layer"),
-        LinearSpec("attn.proj", 1408, 1408, "fp16", "fp16", T, "layer"),
-        LinearSpec("mlp.fc1", 6144, 1408, "fp16", "fp32", T, "layer"),
-        LinearSpec("mlp.fc2", 1408, 6144, "fp16", "fp16", T, "layer"),
+        LinearSpec("attn.qkv", 4224, 1408, "fp16", "fp32", T, "layer", "norm1"),
+        LinearSpec("attn.proj", 1408, 1408, "fp16", "fp16", T, "layer", "attn_ctx"),
+        LinearSpec("mlp.fc1", 6144, 1408, "fp16", "fp32", T, "layer", "norm2"),
+        LinearSpec("mlp.fc2", 1408, 6144, "fp16", "fp16", T, "layer", "gelu"),
     ))
 
 
@@ -39,17 +40,19 @@ def t5_xl_block(i, decoder, batch=8, enc_tokens=64, dec_tokens=32, prefix="t5_mo
     d, ff = 2048, 5120
     Tq = batch * (dec_tokens if decoder else enc_tokens)
     Tkv = batch * enc_tokens
-    lin = [LinearSpec(f"layer.0.SelfAttention.{n}", d, d, "bf16", "bf16", Tq, "row") for n in "qkvo"]
+    # q/k/v are fed the same normed hidden states, wi_0/wi_1 the same FF input, cross-attention k/v the encoder output
+    lin = [LinearSpec(f"layer.0.SelfAttention.{n}", d, d, "bf16", "bf16", Tq, "row", "sa_ctx" if n == "o" else "sa_in")
+           for n in "qkvo"]
     j = 1
     if decoder:
-        lin += [LinearSpec("layer.1.EncDecAttention.q", d, d, "bf16", "bf16", Tq, "row"),
-                LinearSpec("layer.1.EncDecAttention.k", d, d, "bf16", "bf16", Tkv, "row"),
-                LinearSpec("layer.1.EncDecAttention.v", d, d, "bf16", "bf16", Tkv, "row"),
-                LinearSpec("layer.1.EncDecAttention.o", d, d, "bf16", "bf16", Tq, "row")]
+        lin += [LinearSpec("layer.1.EncDecAttention.q", d, d, "bf16", "bf16", Tq, "row", "ca_in"),
+                LinearSpec("layer.1.EncDecAttention.k", d, d, "bf16", "bf16", Tkv, "row", "enc_out"),
+                LinearSpec("layer.1.EncDecAttention.v", d, d, "bf16", "bf16", Tkv, "row", "enc_out"),
+                LinearSpec("layer.1.EncDecAttention.o", d, d, "bf16", "bf16", Tq, "row", "ca_ctx")]
         j = 2
-    lin += [LinearSpec(f"layer.{j}.DenseReluDense.wi_0", ff, d, "bf16", "bf16", Tq, "row"),
-            LinearSpec(f"layer.{j}.DenseReluDense.wi_1", ff, d, "bf16", "bf16", Tq, "row"),
-            LinearSpec(f"layer.{j}.DenseReluDense.wo", d, ff, "bf16", "bf16", Tq, "row")]
+    lin += [LinearSpec(f"layer.{j}.DenseReluDense.wi_0", ff, d, "bf16", "bf16", Tq, "row", "ff_in"),
+            LinearSpec(f"layer.{j}.DenseReluDense.wi_1", ff, d, "bf16", "bf16", Tq, "row", "ff_in"),
+            LinearSpec(f"layer.{j}.DenseReluDense.wo", d, ff, "bf16", "bf16", Tq, "row", "ff_mid")]
     stack = "decoder" if decoder else "encoder"
     return BlockSpec(f"{prefix}.{stack}.block.{i}", tuple(lin))
 
@@ -66,10 +69,11 @@ def llama7b_blocks(batch=1, tokens=2048) -> List[BlockSpec]:
     T = batch * tokens
     out = []
     for i in range(32):
-        lin = [LinearSpec(f"self_attn.{n}_proj", 4096, 4096, "fp16", "fp16", T, "row") for n in "qkvo"]
-        lin += [LinearSpec("mlp.gate_proj", 11008, 4096, "fp16", "fp16", T, "row"),
-                LinearSpec("mlp.up_proj", 11008, 4096, "fp16", "fp16", T, "row"),
-                LinearSpec("mlp.down_proj", 4096, 11008, "fp16", "fp16", T, "row")]
+        lin = [LinearSpec(f"self_attn.{n}_proj", 4096, 4096, "fp16", "fp16", T, "row", "attn_ctx" if n == "o" else "norm1")
+               for n in "qkvo"]
+        lin += [LinearSpec("mlp.gate_proj", 11008, 4096, "fp16", "fp16", T, "row", "norm2"),
+                LinearSpec("mlp.up_proj", 11008, 4096, "fp16", "fp16", T, "row", "norm2"),
+                LinearSpec("mlp.down_proj", 4096, 11008, "fp16", "fp16", T, "row", "act")]
         out.append(BlockSpec(f"model.layers.{i}", tuple(lin)))
     return out
 
@@ -87,9 +91,21 @@ def select_bytes(l: LinearSpec) -> int:
     return 2 * l.rows * l.cols * BYTES[l.w_dtype] + 4 * l.cols
 
 
+def unique_norm_bytes(blocks, n_batches: int) -> int:
+    """Bytes of DISTINCT hook-input tensors per pass (what HBM must deliver when q/k/v etc. share their input)."""
+    tot = 0
+    for b in blocks:
+        seen = {}
+        for l in b.linears:
+            seen[l.src or l.name] = l.tokens * l.cols * BYTES[l.x_dtype]
+        tot += n_batches * sum(seen.values())
+    return tot
+
+
 def summarize(blocks, n_batches):
     lin = [l for b in blocks for l in b.linears]
     return {
+        "unique_norm_input_bytes": unique_norm_bytes(blocks, n_batches),
         "linears": len(lin),
         "params": sum(l.rows * l.cols for l in lin),
         "calib_tokens_per_step": sum(l.tokens * n_batches for l in lin),

@@ -75,11 +75,32 @@ ECF_API size_t ecf_workspace_bytes(int op, int64_t R, int64_t C);
  * (CoOp/trainers/pruners/wanda_pruner.py:159-172, UPop/pruners/wanda_pruner.py:65-78).
  *   scaler_row[c] = scaler_row[c] * rescale + (sum_t x[t,c]^2) * inv_n
  * x is the hook input flattened to [T, C]; the host passes rescale = n/(n+B), inv_n = 1/(n+B).
- * fp32 accumulation, deterministic summation order.  The first 4 KB of `ws` hold self-resetting tickets: zero
+ * fp32 accumulation, deterministic summation order.  The first 64 KB of `ws` hold self-resetting tickets: zero
  * them once before the first call and do not share this workspace with other ops. */
 ECF_API int ecf_sqnorm_accum(const void* x, int x_dtype, int64_t T, int64_t C, int64_t ld,
                      float* scaler_row, float rescale, float inv_n,
                      void* ws, size_t ws_bytes, ecf_stream_t stream);
+
+/* A1, batched -- many hook calls in ONE launch (the reference fires one hook per Linear per calibration batch:
+ * wanda_pruner.py:238-253 registers them, :71-84 is the body).  `descs` is a HOST array of n <= ECF_SQNORM_MAX_BATCH
+ * descriptors; each is one (hook input, accumulator) pair with the same meaning as the arguments of
+ * ecf_sqnorm_accum.  Descriptors may share x (q/k/v, wi_0/wi_1 see the same input).  Descriptors may also share
+ * scaler_row (successive calibration batches of one Linear; same C and dtype; at most 32 distinct accumulators per
+ * launch): they are applied in array order, i.e. the result equals the sequential calls up to fp32 rounding.
+ * Workspace: ecf_sqnorm_batched_workspace_bytes(descs, n); its first 64 KB hold self-resetting tickets (zero
+ * them once before the first call; do not share the workspace with other ops or streams). */
+#define ECF_SQNORM_MAX_BATCH 256
+typedef struct ecf_sqnorm_desc {
+  const void* x;      /* [T, C] activations, row-major, leading dimension ld (elements) */
+  float* scaler_row;  /* [C] fp32 accumulator, updated in place                         */
+  int64_t T, C, ld;
+  int32_t dtype;      /* enum ecf_dtype of x */
+  float rescale;      /* n / (n + B)  */
+  float inv_n;        /* 1 / (n + B)  */
+} ecf_sqnorm_desc;
+ECF_API size_t ecf_sqnorm_batched_workspace_bytes(const ecf_sqnorm_desc* descs, int n);
+ECF_API int ecf_sqnorm_accum_batched(const ecf_sqnorm_desc* descs, int n,
+                             void* ws, size_t ws_bytes, ecf_stream_t stream);
 
 /* A3+A4+A7 -- per-ROW Wanda select, wanda_pruner.py:260,272-279 (T5); CoOp wanda_pruner.py:357,
  * 379-383 (CLIP); UPop wanda_pruner.py:243,253-260 (BERT); LLaMA/image_classifiers/prune_utils.py:35-38.

@@ -92,6 +92,79 @@ def test_sqnorm_noncontiguous_rows_and_determinism():
     np.testing.assert_allclose(f32(a), orc.sqnorm_columns(f32(view)), rtol=2e-5)
 
 
+def test_sqnorm_batched_matches_single_calls_bitwise():
+    """One launch over the Linears of a block (mixed dtypes / widths / token counts, q-k-v sharing one input, a ragged
+    scalar-path shape) against the per-hook launches."""
+    from ecoflap_b200 import ops
+
+    g = torch.Generator().manual_seed(11)
+    xs = {
+        "ln1": torch.randn(8 * 257, 1408, generator=g),                       # fp32 LayerNorm output -> qkv
+        "attn": torch.randn(8 * 257, 1408, generator=g).half(),               # fp16 -> proj
+        "ln2": torch.randn(8 * 257, 1408, generator=g),                       # fp32 -> fc1
+        "gelu": torch.randn(8 * 257, 6144, generator=g).half(),               # fp16 -> fc2
+        "t5": torch.randn(512, 2048, generator=g).bfloat16(),                 # shared by q, k, v
+        "ragged": torch.randn(77, 50, generator=g).bfloat16(),                # scalar path
+    }
+    xs = {k: v.to(dev()) for k, v in xs.items()}
+    plan = ["ln1", "attn", "ln2", "gelu", "t5", "t5", "t5", "ragged"]
+    start = [torch.rand(xs[k].shape[1], generator=g).to(dev()) for k in plan]
+    single = [s.clone() for s in start]
+    batched = [s.clone() for s in start]
+    for k, s in zip(plan, single):
+        ops.sqnorm_accum(xs[k], s, 0.75, 0.125)
+    ops.sqnorm_accum_batched([(xs[k], s, 0.75, 0.125) for k, s in zip(plan, batched)])
+    again = [s.clone() for s in start]
+    ops.sqnorm_accum_batched([(xs[k], s, 0.75, 0.125) for k, s in zip(plan, again)])
+    for k, a, b, c in zip(plan, single, batched, again):
+        assert torch.equal(b, c), k  # a launch plan has one fixed summation order: bit-identical run to run
+        # the split of the token range differs between the two plans, so only the fp32 rounding may differ
+        np.testing.assert_allclose(f32(a), f32(b), rtol=2e-6, atol=1e-30, err_msg=k)
+    # successive calibration batches of ONE accumulator inside one launch == the sequential running mean
+    seq, merged = start[4].clone(), start[4].clone()
+    calls, n = [], 24
+    for i in range(5):
+        x = (torch.randn(64 + 37 * i, 2048, generator=g) * (1 + i)).bfloat16().to(dev())
+        b = 1 + i % 3
+        calls.append((x, n / (n + b), 1.0 / (n + b)))
+        n += b
+    for x, r, w in calls:
+        ops.sqnorm_accum(x, seq, r, w)
+    ops.sqnorm_accum_batched([(x, merged, r, w) for x, r, w in calls])
+    np.testing.assert_allclose(f32(merged), f32(seq), rtol=5e-6, atol=1e-30)
+    with pytest.raises(Exception):  # one accumulator, two widths
+        ops.sqnorm_accum_batched([(xs["t5"], batched[4], 0.0, 1.0), (xs["ragged"], batched[4][:50], 0.0, 1.0)])
+
+
+def test_norm_batch_accumulator_equals_reference_running_mean():
+    """WrappedGPT with a NormBatch (deferred, one launch per block forward) against the oracle's running mean, incl.
+    more descriptors than one launch takes and the same accumulator hit twice before a flush."""
+    from ecoflap_b200.accumulators import NormBatch, WrappedGPT
+
+    g = torch.Generator().manual_seed(3)
+    nb = NormBatch()
+    lins = [torch.nn.Linear(256, 8, bias=False).to(dev()).half() for _ in range(40)]
+    accs = [WrappedGPT(l, batch=nb) for l in lins]
+    refs = [orc.NormAccumulator(256) for _ in lins]
+    for _ in range(3):
+        x = torch.randn(4, 19, 256, generator=g).half()
+        for a, r in zip(accs, refs):
+            a.add_batch(x.to(dev()))
+            r.add_batch(x.float().numpy())
+        accs[0].add_batch(x.to(dev()))  # second hit on the same accumulator inside one forward
+        refs[0].add_batch(x.float().numpy())
+        nb.flush()
+    assert len(nb) == 0
+    for a, r in zip(accs, refs):
+        assert a.nsamples == r.nsamples
+        np.testing.assert_allclose(f32(a.scaler_row), r.scaler_row, rtol=1e-4)
+    x = torch.randn(2, 5, 256, generator=g).half().to(dev())
+    accs[1].add_batch(x)
+    x.mul_(2.0)  # in-place change between hook and flush must be detected, not silently mis-accumulated
+    with pytest.raises(RuntimeError):
+        nb.flush()
+
+
 # ---------------------------------------------------------------------------- A3+A4+A7
 ROW_SHAPES = [(64, 2048), (48, 5120), (40, 4096), (24, 11008), (96, 768), (33, 1408), (16, 512), (7, 96), (5, 50), (4, 8)]
 

@@ -10,7 +10,29 @@ R, C = int(sys.argv[2]), int(sys.argv[3])
 dt = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[sys.argv[4]]
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 torch.manual_seed(0)
-if which == "sqnorm":
+if which in ("sqnorm_vit", "sqnorm_t5"):
+    # the batched norm launch of one block forward at BLIP-2 shapes (R, C, dtype arguments are ignored)
+    if which == "sqnorm_vit":
+        shapes = [(2056, 1408, torch.float32), (2056, 1408, torch.float16), (2056, 1408, torch.float32), (2056, 6144, torch.float16)]
+        share = [0, 1, 2, 3]
+    else:
+        shapes = [(512, 2048, torch.bfloat16), (512, 2048, torch.bfloat16), (512, 2048, torch.bfloat16), (512, 5120, torch.bfloat16)]
+        share = [0, 0, 0, 1, 2, 2, 3]
+    xs = [torch.randn(t, c, device=dev).to(d) for t, c, d in shapes]
+    items = [(xs[i], torch.zeros(xs[i].shape[1], device=dev), 0.5, 0.5) for i in share]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(reps):
+        flush.zero_()
+        ops.sqnorm_accum_batched(items)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ops.sqnorm_accum_batched(items); ops.sqnorm_accum_batched(items); ops.sqnorm_accum_batched(items); ops.sqnorm_accum_batched(items); e1.record()
+        torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1) / 4)
+    print(which, "us per launch (4 back to back, 1st cold):", sorted(ts)[len(ts) // 2] * 1e3)
+elif which == "sqnorm":
     x = torch.randn(R, C, device=dev).to(dt)
     s = torch.zeros(C, device=dev)
     for _ in range(reps):
