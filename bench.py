@@ -269,30 +269,31 @@ def run_b200(args):
                 for o, acc in zip(pb, accs):
                     acc.add_batch(o.acts[j])
             nb.flush()
+            layer_items = [(o.W, acc.scaler_row, o.idx) for o, acc in zip(pb, accs) if o.spec.select == "layer"]
             if world > 1:
                 edist.sync_block_norms(accs)
                 for o, acc in zip(pb, accs):
                     if o.spec.select == "row":
                         edist.row_sharded_select(o.W, lambda sh, a=acc, k=o.k: ops.wanda_row_select_apply(sh, a.scaler_row, k))
-                    else:
-                        ops.wanda_layer_thresh_apply(o.W, acc.scaler_row, o.idx)
+                if layer_items:
+                    ops.wanda_layer_thresh_apply_batched(layer_items)
                 continue
-            for i, (o, acc) in enumerate(zip(pb, accs)):
+            if layer_items:  # the per-layer selects of a block: one cooperative launch
+                ops.wanda_layer_thresh_apply_batched(layer_items)
+            rows = [(o, acc) for o, acc in zip(pb, accs) if o.spec.select == "row"]
+            for i, (o, acc) in enumerate(rows):
                 st = side[i]
                 st.wait_stream(main)
                 with torch.cuda.stream(st):
-                    if o.spec.select == "row":
-                        ops.wanda_row_select_apply(o.W, acc.scaler_row, o.k)
-                    else:
-                        ops.wanda_layer_thresh_apply(o.W, acc.scaler_row, o.idx)
-            for i in range(len(pb)):
+                    ops.wanda_row_select_apply(o.W, acc.scaler_row, o.k)
+            for i in range(len(rows)):
                 main.wait_stream(side[i])
 
     launches_per_step = 0
     for pb in lins:
         launches_per_step += -(-(N_BATCHES * len(pb)) // _abi.SQNORM_MAX_BATCH)  # batched norm launches per block
-        for o in pb:
-            launches_per_step += 1 if o.spec.select == "row" else 7
+        launches_per_step += sum(1 for o in pb if o.spec.select == "row")
+        launches_per_step += 1 if any(o.spec.select == "layer" for o in pb) else 0  # batched cooperative select
 
     def barrier():
         if world > 1:
@@ -390,15 +391,22 @@ def run_b200(args):
         fam["sqnorm"][0] += ms
         fam["sqnorm"][1] += sum(wl.norm_bytes(o.spec, N_BATCHES) for o in pb)
         fam["sqnorm"][2] += -(-len(items) // _abi.SQNORM_MAX_BATCH)
+        layer = [(o, acc) for o, acc in zip(pb, accs) if o.spec.select == "layer"]
+        if layer:
+            items_l = [(o.W, acc.scaler_row, o.idx) for o, acc in layer]
+            ms = timed_graph(lambda: ops.wanda_layer_thresh_apply_batched(items_l),
+                             prepare=lambda: [o.W.copy_(o.W0) for o, _ in layer])
+            fam["layer_thresh"][0] += ms
+            fam["layer_thresh"][1] += sum(wl.select_bytes(o.spec) for o, _ in layer)
+            fam["layer_thresh"][2] += 1
         for o, acc in zip(pb, accs):
-            if o.spec.select == "row":
-                name, fn, nl = "row_select", (lambda o=o, acc=acc: ops.wanda_row_select_apply(o.W, acc.scaler_row, o.k)), 1
-            else:
-                name, fn, nl = "layer_thresh", (lambda o=o, acc=acc: ops.wanda_layer_thresh_apply(o.W, acc.scaler_row, o.idx)), 7
-            ms = timed_graph(fn, prepare=lambda o=o: o.W.copy_(o.W0))
-            fam[name][0] += ms
-            fam[name][1] += wl.select_bytes(o.spec)
-            fam[name][2] += nl
+            if o.spec.select != "row":
+                continue
+            ms = timed_graph(lambda o=o, acc=acc: ops.wanda_row_select_apply(o.W, acc.scaler_row, o.k),
+                             prepare=lambda o=o: o.W.copy_(o.W0))
+            fam["row_select"][0] += ms
+            fam["row_select"][1] += wl.select_bytes(o.spec)
+            fam["row_select"][2] += 1
     del scratch
     kernels = {}
     for name, (ms, nbytes, n) in fam.items():

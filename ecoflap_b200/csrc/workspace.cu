@@ -3,7 +3,7 @@
 
 namespace ecf {
 size_t sqnorm_workspace_bytes(int64_t T, int64_t C);
-size_t layer_thresh_workspace_bytes();
+size_t layer_thresh_workspace_bytes(int64_t R, int64_t C);
 size_t group_reduce_workspace_bytes(int64_t total_chunks);
 size_t hessian_workspace_bytes(int64_t T, int64_t C);
 size_t obs_workspace_bytes(int64_t R, int64_t C);
@@ -15,7 +15,7 @@ extern "C" size_t ecf_workspace_bytes(int op, int64_t R, int64_t C) {
   switch (op) {
     case ECF_OP_SQNORM: return sqnorm_workspace_bytes(R, C);
     case ECF_OP_ROW_SELECT: return 256;  // none needed; a non-zero size keeps callers uniform
-    case ECF_OP_LAYER_THRESH: return layer_thresh_workspace_bytes();
+    case ECF_OP_LAYER_THRESH: return layer_thresh_workspace_bytes(R, C);
     case ECF_OP_GROUP_REDUCE: return group_reduce_workspace_bytes(C);
     case ECF_OP_HESSIAN: return hessian_workspace_bytes(R, C);
     case ECF_OP_OBS: return obs_workspace_bytes(R, C);

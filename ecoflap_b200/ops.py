@@ -152,6 +152,40 @@ def wanda_layer_thresh_apply(W, scaler_row, kth_index: int, thres_out=None, mask
         n_zero.data_ptr() if n_zero is not None else None, ws.data_ptr(), ws.numel(), _stream(W)))
 
 
+def wanda_layer_thresh_apply_batched(items) -> None:
+    """Per-layer select of several matrices (the Linears of one block) in one cooperative launch.  ``items`` is a list
+    of ``(W, scaler_row, kth_index)`` or ``(W, scaler_row, kth_index, thres_out, mask_bits, n_zero)`` tuples; lists
+    longer than the ABI's batch limit are issued as several launches."""
+    items = [tuple(it) + (None,) * (6 - len(it)) for it in items]
+    for start in range(0, len(items), _abi.LAYER_MAX_BATCH):
+        chunk = items[start:start + _abi.LAYER_MAX_BATCH]
+        descs = (_abi.LayerDesc * len(chunk))()
+        for d, (W, scaler_row, kth, thres_out, mask_bits, n_zero) in zip(descs, chunk):
+            _require_cuda(W, scaler_row, mask_bits, n_zero, thres_out)
+            R, C, ld = _weight_2d(W)
+            assert scaler_row.dtype == torch.float32 and scaler_row.numel() == C and scaler_row.is_contiguous()
+            if not (0 <= kth < R * C):
+                raise IndexError(f"index {kth} is out of bounds for dimension 0 with size {R * C}")
+            d.W, d.scaler_row, d.R, d.C, d.ld, d.dtype, d.kth_index = W.data_ptr(), scaler_row.data_ptr(), R, C, ld, dtype_code(W), int(kth)
+            d.thres_out = thres_out.data_ptr() if thres_out is not None else None
+            d.mask_bits = mask_bits.data_ptr() if mask_bits is not None else None
+            d.mask_ld = mask_bits.stride(0) if mask_bits is not None else 0
+            d.n_zero = n_zero.data_ptr() if n_zero is not None else None
+        dev = chunk[0][0].device
+        need = lib.ecf_layer_thresh_batched_workspace_bytes(descs, len(chunk))
+        ws = _ws.get(dev, need, "layer_thresh")
+        check(lib.ecf_wanda_layer_thresh_apply_batched(descs, len(chunk), ws.data_ptr(), ws.numel(), _stream(chunk[0][0])))
+
+
+def layer_thresh_phase_times_us(device) -> list:
+    """Profiling aid: durations (us) of the phases P1..P5 of the LAST batched per-layer select on the current stream
+    of ``device`` (read from the %globaltimer stamps the kernel leaves at the start of its workspace).  Synchronises."""
+    torch.cuda.synchronize(device)
+    ws = _ws.get(device, 256, "layer_thresh")
+    t = ws[:48].view(torch.int64).tolist()
+    return [(b - a) / 1e3 for a, b in zip(t[:-1], t[1:])]
+
+
 def zo_perturb(W: torch.Tensor, z: torch.Tensor, scaling: float, eps: float) -> None:
     """W = rn(W + rn(rn(scaling*z)*eps)) in W's dtype, in place (A11)."""
     _require_cuda(W, z)

@@ -195,6 +195,7 @@ def sweep_blocks(pruner, model, dataloader, device, spec: SweepSpec, model_prefi
             for h in handles:
                 h.remove()
 
+        layer_items = []
         for name in subset:
             assert wrapped[name].nsamples == spec.expected_nsamples(inps), (
                 f"{name}: accumulated {wrapped[name].nsamples} samples, expected {spec.expected_nsamples(inps)}")
@@ -202,12 +203,18 @@ def sweep_blocks(pruner, model, dataloader, device, spec: SweepSpec, model_prefi
             key = spec.sparsity_key(module_to_process, i, name)
             if pruner.prune_n != 0:
                 raise NotImplementedError("n:m sparsity is dead code in the reference (prune_n = prune_m = 0)")
-            if method == "wanda":
+            if method == "wanda" and spec.select == "layer":
+                # every Linear of the block keeps its own exact threshold; they are selected in one cooperative launch
+                W = subset[name].weight.data
+                layer_items.append((W, wrapped[name].scaler_row, int(W.numel() * sparsity_ratio[key])))
+            elif method == "wanda":
                 wanda_prune_linear(subset[name], wrapped[name], sparsity_ratio[key], spec.select)
             else:
                 wrapped[name].fasterprune(sparsity_ratio[key], prune_n=pruner.prune_n, prune_m=pruner.prune_m,
                                           percdamp=0.01, blocksize=128)
                 wrapped[name].free()
+        if layer_items:
+            ops.wanda_layer_thresh_apply_batched(layer_items)
         if restore is not None:
             restore()
 

@@ -122,6 +122,27 @@ ECF_API int ecf_wanda_layer_thresh_apply(void* W, int w_dtype, int64_t R, int64_
                                  uint8_t* mask_bits, int64_t mask_ld, unsigned long long* n_zero,
                                  void* ws, size_t ws_bytes, ecf_stream_t stream);
 
+/* A3+A5+A7, batched -- the per-layer select of all the Linears of a block (ViT: qkv, proj, fc1, fc2) in ONE
+ * cooperative launch; every matrix gets its own exact threshold exactly as in ecf_wanda_layer_thresh_apply
+ * (the reference prunes them one after the other: wanda_pruner.py:536-558).  `descs` is a HOST array of
+ * n <= ECF_LAYER_MAX_BATCH distinct matrices.  Workspace: ecf_layer_thresh_batched_workspace_bytes(descs, n),
+ * zeroed once before its first use, not shared with other ops or streams. */
+#define ECF_LAYER_MAX_BATCH 8
+typedef struct ecf_layer_desc {
+  void* W;                    /* [R, C] weights, row-major, leading dimension ld (elements); pruned in place */
+  const float* scaler_row;    /* [C] fp32 */
+  int64_t R, C, ld;
+  int32_t dtype;              /* enum ecf_dtype of W */
+  int64_t kth_index;          /* int(numel * s), host-computed */
+  float* thres_out;           /* nullable: device float receiving the threshold */
+  uint8_t* mask_bits;         /* nullable: packed mask, row stride mask_ld bytes */
+  int64_t mask_ld;
+  unsigned long long* n_zero; /* nullable: += zero-valued weights after the call */
+} ecf_layer_desc;
+ECF_API size_t ecf_layer_thresh_batched_workspace_bytes(const ecf_layer_desc* descs, int n);
+ECF_API int ecf_wanda_layer_thresh_apply_batched(const ecf_layer_desc* descs, int n,
+                                         void* ws, size_t ws_bytes, ecf_stream_t stream);
+
 /* A14 -- group aggregation, layer_single_base_pruner.py:361-377 together with the |W| / W^2 factors
  * of :467,:556-559.  One launch over a DEVICE table of tensors; per tensor i:
  *   sum_abs[i] = sum |w|,  sum_sq[i] = sum w^2      (fp32 partials, fp64 final combine)

@@ -345,6 +345,62 @@ def test_layer_thresh_bit_exact(dt, shape):
         assert int(nz.item()) == orc.count_zero(Wref)
 
 
+def test_layer_thresh_batched_block_and_full_size():
+    """The four Linears of an EVA ViT-g block (full BASELINE.json sizes) in one cooperative launch: every matrix gets
+    its own exact threshold; checked against the oracle on the small ones and through the defining properties
+    (threshold is the kth order statistic; mask == score <= thres) on all of them."""
+    from ecoflap_b200 import ops
+
+    shapes = [(4224, 1408), (1408, 1408), (6144, 1408), (1408, 6144)]
+    Ws = [synth_w(R, C, "fp16", seed=R + C).to(dev()) for R, C in shapes]
+    W0 = [w.clone() for w in Ws]
+    ss = [torch.from_numpy(synth_norm(C, seed=i + 3)).to(dev()) for i, (R, C) in enumerate(shapes)]
+    th = [torch.zeros(1, device=dev()) for _ in shapes]
+    mbs = [ops.alloc_mask_bits(R, C, dev()) for R, C in shapes]
+    nzs = [torch.zeros(1, dtype=torch.int64, device=dev()) for _ in shapes]
+    sp = [0.5, 0.41999998688697815, 0.6, 0.3]
+    idx = [orc.layer_kth_index(R * C, s) for (R, C), s in zip(shapes, sp)]
+    ops.wanda_layer_thresh_apply_batched([(w, s, k, t, m, z) for w, s, k, t, m, z in zip(Ws, ss, idx, th, mbs, nzs)])
+    for i, (R, C) in enumerate(shapes):
+        score = W0[i].float().abs() * ss[i].sqrt()[None, :]
+        kth = torch.kthvalue(score.flatten(), idx[i] + 1).values
+        assert float(th[i].item()) == float(kth.item()), i
+        mask = score <= kth
+        assert torch.equal(ops.unpack_mask_bits(mbs[i], C), mask)
+        assert torch.equal(Ws[i], torch.where(mask, torch.zeros_like(W0[i]), W0[i]))
+        assert int(nzs[i].item()) == int((Ws[i] == 0).sum().item())
+    Wref, _, thres = orc.wanda_prune_layer(f32(W0[1]), ss[1].cpu().numpy(), sp[1])
+    assert float(th[1].item()) == float(thres) and np.array_equal(f32(Ws[1]), Wref)
+
+
+@pytest.mark.parametrize("dt", ["fp16", "bf16", "fp32"])
+def test_layer_thresh_heavy_ties_outside_the_sampled_bracket(dt):
+    """half the matrix already zero / constant / duplicated: the k-th score sits in a huge tie class, which makes the
+    sampled bracket wide (or wrong) and exercises the retry and the 3-digit refinement."""
+    from ecoflap_b200 import ops
+
+    R, C = 1024, 768
+    for case in range(4):
+        W = synth_w(R, C, dt, seed=case + 40)
+        if case == 0:
+            W[::2] = 0
+        elif case == 1:
+            W[:] = W[0, 0]
+        elif case == 2:
+            W[:, C // 2:] = W[:, : C // 2]
+        else:
+            W[:, 5] = float("inf")
+        s = synth_norm(C, seed=case) if case != 1 else np.full(C, 2.0, dtype=np.float32)
+        for sparsity in (0.5, 0.25, 0.9, 0.001):
+            idx = orc.layer_kth_index(R * C, sparsity)
+            Wd = W.clone().to(dev())
+            th = torch.zeros(1, device=dev())
+            ops.wanda_layer_thresh_apply(Wd, torch.from_numpy(s).to(dev()), idx, thres_out=th)
+            Wref, _, thres = orc.wanda_prune_layer(f32(W), s, sparsity)
+            assert float(th.item()) == float(thres), (dt, case, sparsity)
+            assert np.array_equal(np.nan_to_num(f32(Wd), posinf=1e38), np.nan_to_num(Wref, posinf=1e38)), (dt, case, sparsity)
+
+
 def test_layer_thresh_ties_and_range():
     from ecoflap_b200 import ops
 

@@ -10,7 +10,22 @@ R, C = int(sys.argv[2]), int(sys.argv[3])
 dt = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[sys.argv[4]]
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 torch.manual_seed(0)
-if which in ("sqnorm_vit", "sqnorm_t5"):
+if which == "layer_block":
+    shapes = [(4224, 1408), (1408, 1408), (6144, 1408), (1408, 6144)]
+    W0 = [(torch.randn(r, c, device=dev) * 0.02).half() for r, c in shapes]
+    ss = [torch.rand(c, device=dev) + 0.1 for r, c in shapes]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(reps):
+        Ws = [w.clone() for w in W0]
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.wanda_layer_thresh_apply_batched([(w, s, w.numel() // 2) for w, s in zip(Ws, ss)])
+        e1.record()
+        torch.cuda.synchronize()
+        print("block select ms", e0.elapsed_time(e1), "phase us (sample, bracket, count, refine, apply):",
+              [round(x, 1) for x in ops.layer_thresh_phase_times_us(dev)])
+elif which in ("sqnorm_vit", "sqnorm_t5"):
     # the batched norm launch of one block forward at BLIP-2 shapes (R, C, dtype arguments are ignored)
     if which == "sqnorm_vit":
         shapes = [(2056, 1408, torch.float32), (2056, 1408, torch.float16), (2056, 1408, torch.float32), (2056, 6144, torch.float16)]
@@ -46,4 +61,5 @@ else:
             ops.wanda_row_select_apply(W, s, C // 2)
         else:
             ops.wanda_layer_thresh_apply(W, s, R * C // 2)
+            print("phase us (sample, bracket, count, refine, apply):", [round(x, 1) for x in ops.layer_thresh_phase_times_us(dev)])
 torch.cuda.synchronize()
