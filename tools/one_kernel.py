@@ -47,6 +47,38 @@ elif which in ("sqnorm_vit", "sqnorm_t5"):
         e0.record(); ops.sqnorm_accum_batched(items); ops.sqnorm_accum_batched(items); ops.sqnorm_accum_batched(items); ops.sqnorm_accum_batched(items); e1.record()
         torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1) / 4)
     print(which, "us per launch (4 back to back, 1st cold):", sorted(ts)[len(ts) // 2] * 1e3)
+elif which == "hessian":
+    # R = tokens T, C = channels; X^T X on tcgen05 (A8)
+    x = torch.randn(R, C, device=dev).to(dt)
+    H = torch.zeros(C, C, device=dev)
+    for _ in range(2):
+        ops.hessian_accum(x, H, 0.5, 0.5)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ops.hessian_accum(x, H, 0.5, 0.5); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    print(f"hessian T={R} C={C} {sys.argv[4]}: {ms*1e3:.1f} us, {2*R*C*C/ms/1e9:.1f} TFLOP/s algorithmic (full product)")
+elif which == "obs":
+    # full OBS block loop (A10) on an R x C fp32 working copy with a well-conditioned upper factor
+    from ecoflap_b200.accumulators import SparseGPT
+    lin = torch.nn.Linear(C, R, bias=False).to(dev).to(dt)
+    xs = torch.randn(max(2 * C, 4096), C, device=dev).to(dt)
+    ts = []
+    for _ in range(reps):
+        with torch.no_grad():
+            lin.weight.copy_(torch.randn(R, C, device=dev) * 0.02)
+        sg = SparseGPT(lin)
+        sg.add_batch(xs.unsqueeze(0))
+        W = lin.weight.data.float().contiguous()
+        Hinv, dead = sg.prepare_hinv(0.01)
+        kth = [int(R * min(128, C - i) * 0.5) for i in range(0, C, 128)]
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ops.obs_prune(W, Hinv, kth, 128); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    print(f"obs R={R} C={C}: {ms:.3f} ms, trailing-update {R*C*C/ms/1e9:.2f} TFLOP/s algorithmic")
 elif which == "sqnorm":
     x = torch.randn(R, C, device=dev).to(dt)
     s = torch.zeros(C, device=dev)
