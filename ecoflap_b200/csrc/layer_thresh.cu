@@ -8,20 +8,21 @@
 // these sizes (2-17 MB per matrix, a few microseconds of HBM time) every kernel boundary costs as much as the data.
 // So ONE persistent cooperative kernel serves all the matrices of a block (ViT-g: qkv, proj, fc1, fc2 = 50 MB) and
 // moves through its phases with grid barriers:
-//   P1  sample   1 vector in S of every matrix -> 32 768-bin histogram of the upper 16 key bits (global REDs on
-//                <= 131 072 samples per matrix); the same phase writes q = sqrt(scaler_row) once per column
+//   P1  sample   1 vector in S of every matrix (all matrices in one flat index space) -> 31 744-bin histogram of the
+//                upper 16 key bits (global REDs on <= 131 072 samples per matrix); also q = sqrt(scaler_row)
 //   P2  bracket  one CTA per matrix scans its histogram: coarse bracket [lo, hi) = sample ranks k_s -+ 2.5 sqrt(n_s)
-//   P3  count    the only HBM read of W: #(key < lo) in registers + 2 048-bin histogram of the top digit of
-//                (key - lo) for the ~1-2 % of elements inside the bracket (shared-memory atomics are affordable
-//                there: they retire ~0.5 elements/clk/SM, a full-matrix histogram would need ~12)
-//   P4  refine   (1-2 times, W now L2 resident) next 11-bit digit of the elements matching the prefix
+//   P3  count    the only HBM read of W.  Per 8-element vector: exact fp32 scores -> upper 16 bits packed two per
+//                register (clamped to the finite fp16 range, so HSET2 compares them like integers) -> #(key < lo)
+//                by mask popcounts, and "has an element in [lo, hi)" as one bit.  Vectors with that bit (~10 %) are
+//                only APPENDED to a per-CTA shared-memory list; the CTA then walks its list with all lanes busy and
+//                histograms the top 11-bit digit of the ~1-2 % of elements inside the bracket (shared atomics are
+//                affordable there, a full-matrix histogram is not: ~2 clk per element per SM)
+//   P4  refine   the next digit(s) come from the SAME per-CTA lists (no second pass over W)
 //   P5  apply    score <= thres -> zero, in place (L2 read, HBM write); optional packed mask / zero count
-// (grid barriers: cooperative_groups grid.sync(), the launch is cooperative so all CTAs are co-resident)
-// If the k-th score falls outside the sampled bracket (probability ~1e-6, or adversarial ties) the bracket is
-// replaced by the side that holds it and P3 is repeated -- the result is always exact.
+// A CTA whose list overflows (heavy ties inside the bracket) histograms those vectors on the spot and re-scans its
+// share of W for the later digits -- slower, still exact.  If the k-th score falls outside the sampled bracket
+// (probability ~1e-6, or adversarial ties) the bracket is replaced by the side that holds it and P3 is repeated.
 // Bound: HBM.  Algorithmic bytes per matrix: 2*R*C*sizeof(w) + 4*C (re-reads are L2 hits).
-#include <cooperative_groups.h>
-
 #include "common.cuh"
 
 namespace ecf {
@@ -31,6 +32,12 @@ constexpr int kLtMaxMat = ECF_LAYER_MAX_BATCH;
 constexpr int kLtCoarseBins = 32768;
 constexpr int kLtBins = 2048;
 constexpr int kLtSampleVecs = 16384;  // sampled 8-element vectors per matrix (131 072 scores)
+constexpr int kLtListCap = 6144;      // bracket-vector list per CTA (24 KB of shared memory)
+constexpr uint32_t kLtTop = 0x7c00u;  // end of the coarse key domain: keys are clamped to the finite fp16 patterns
+constexpr int kLtSampWords = kLtTop / 2;        // per-CTA sample histogram: 16-bit counters packed two per word (62 KB)
+constexpr int kLtSampChunk = 4096;              // sampled vectors per CTA between flushes (8 * 4096 < 65 536 per bin)
+constexpr int kLtHeaderBytes = 8192;            // workspace header: phase stamps, grid barrier state
+constexpr int kLtBarMaxGroups = 32;             // grid barrier: two-level arrival tree, one counter per 128 bytes
 
 struct LtMat {
   void* W;
@@ -39,7 +46,7 @@ struct LtMat {
   unsigned* coarse;         // workspace: [kLtCoarseBins] sample histogram (self-cleaning)
   unsigned* hist;           // workspace: [3][kLtBins] digit histograms (self-cleaning)
   unsigned long long* cnt;  // workspace: [0] #(key < lo), [1] #(lo <= key < hi)
-  uint32_t* bracket;        // workspace: [0] lo, [1] hi (coarse, hi exclusive, <= 0x8000), [2] retry flag
+  uint32_t* bracket;        // workspace: [0] lo, [1] hi (coarse, hi exclusive, <= kLtTop), [3] P1 ticket
   float* thres_out;
   uint8_t* mask;
   unsigned long long* n_zero;
@@ -49,15 +56,18 @@ struct LtMat {
   int64_t nvec;             // R * nvpr
   int64_t vec_begin;        // prefix over the matrices of the launch
   int64_t sample_stride;    // S
+  int64_t sample_begin;     // prefix of the sampled vectors over the matrices
   int64_t col_begin;        // prefix of C over the matrices (q-table work split)
+  int64_t step_rows, step_cols;  // grid stride (threads) = step_rows * nvpr + step_cols
   int dtype, aligned;
 };
 
 struct LtBatch {
   LtMat m[kLtMaxMat];
   int n;
-  int64_t total_vec, total_cols;
+  int64_t total_vec, total_cols, total_samples;
   unsigned long long* stamps;  // workspace: %globaltimer of CTA 0 at the phase boundaries (profiling aid)
+  unsigned* bar;               // workspace: [0] generation, [1] top counter, [32 * (1 + g)] counter of arrival group g
 };
 
 __device__ __forceinline__ void lt_stamp(const LtBatch& b, int i) {
@@ -68,72 +78,122 @@ __device__ __forceinline__ void lt_stamp(const LtBatch& b, int i) {
   }
 }
 
-namespace cg = cooperative_groups;
+__device__ __forceinline__ __half2 lt_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t lt_dup(uint32_t p) { return p | (p << 16); }
 
-template <int DT, bool ALIGNED>
-__device__ __forceinline__ void lt_load_chunk(const char* wrow, int64_t c0, int64_t C, uint32_t (&raw)[8]) {
-  // raw[j] = bit pattern of element j widened to 32 bits (fp32 bits, or the 16-bit pattern in the low half)
-  if (ALIGNED) {
-    if constexpr (DT == ECF_F32) {
-      const uint4 a = ldg_v4(wrow + c0 * 4), b = ldg_v4(wrow + c0 * 4 + 16);
-      raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w; raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w;
+// position of a vector inside the launch: matrix, row, column (in 8-element vectors)
+struct LtCur {
+  int mi;
+  uint32_t row, col;  // R and ceil(C / 8) are checked to fit 31 bits on the host
+};
+
+__device__ __forceinline__ void lt_seek(const LtBatch& b, int64_t v, LtCur& c) {
+  int mi = c.mi;
+  while (v >= b.m[mi].vec_begin + b.m[mi].nvec) ++mi;
+  c.mi = mi;
+  const LtMat& M = b.m[mi];
+  const int64_t lv = v - M.vec_begin;
+  if (M.nvec < (1ll << 31)) {  // 32-bit division: every BASELINE.json matrix
+    const uint32_t r32 = (uint32_t)lv / (uint32_t)M.nvpr;
+    c.row = r32;
+    c.col = (uint32_t)lv - r32 * (uint32_t)M.nvpr;
+  } else {
+    const int64_t r64 = lv / M.nvpr;
+    c.row = (uint32_t)r64;
+    c.col = (uint32_t)(lv - r64 * M.nvpr);
+  }
+}
+// advance by one grid stride; v is the NEW flat index (seek again when it leaves the matrix)
+__device__ __forceinline__ void lt_next(const LtBatch& b, int64_t v, LtCur& c) {
+  const LtMat& M = b.m[c.mi];
+  if (v >= M.vec_begin + M.nvec) {
+    if (v < b.total_vec) lt_seek(b, v, c);
+    return;
+  }
+  c.col += (uint32_t)M.step_cols;
+  c.row += (uint32_t)M.step_rows;
+  if (c.col >= (uint32_t)M.nvpr) {
+    c.col -= (uint32_t)M.nvpr;
+    ++c.row;
+  }
+}
+
+// the 16 / 32 bytes of an aligned vector, loaded ahead of their use (software pipelining of the streaming passes)
+struct LtRaw {
+  uint4 a;  // first 16 bytes of the vector (all of it for 16-bit types; fp32 vectors fetch their second half at use)
+};
+__device__ __forceinline__ void lt_issue(const LtMat& M, const LtCur& c, LtRaw& r) {
+  if (!M.aligned) return;
+  const int eb = M.dtype == ECF_F32 ? 4 : 2;
+  const char* p = reinterpret_cast<const char*>(M.W) + ((int64_t)c.row * M.ld + (int64_t)c.col * 8) * eb;
+  r.a = ldg_v4(p);
+}
+
+// Bit patterns u[e] of the exact scores fp32(|w|) * q of vector (row, col); out-of-range columns (ragged C) get
+// 0xffffffff.  raw[] = the weight words (aligned: 4 packed words for 16-bit types, 8 words for fp32), taken from the
+// pre-issued load `r` when the matrix is aligned.
+template <int DT, bool ALIGNED, bool SQRT_INLINE>
+__device__ __forceinline__ void lt_score_bits(const LtMat& M, uint32_t row, uint32_t col, const LtRaw& r, uint32_t (&u)[8],
+                                              uint32_t (&raw)[8]) {
+  const int64_t c0 = (int64_t)col * 8;
+  if constexpr (ALIGNED) {
+    float q[8];
+    if constexpr (SQRT_INLINE) {
+      const float4 sa = *reinterpret_cast<const float4*>(M.s + c0), sb = *reinterpret_cast<const float4*>(M.s + c0 + 4);
+      const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q[j] = __fadd_rn(sqrtf(sv[j]), 0.f);
     } else {
-      const uint4 a = ldg_v4(wrow + c0 * 2);
-      raw[0] = a.x & 0xffffu; raw[1] = a.x >> 16; raw[2] = a.y & 0xffffu; raw[3] = a.y >> 16;
-      raw[4] = a.z & 0xffffu; raw[5] = a.z >> 16; raw[6] = a.w & 0xffffu; raw[7] = a.w >> 16;
+      const float4 qa = *reinterpret_cast<const float4*>(M.q + c0), qb = *reinterpret_cast<const float4*>(M.q + c0 + 4);
+      q[0] = qa.x; q[1] = qa.y; q[2] = qa.z; q[3] = qa.w; q[4] = qb.x; q[5] = qb.y; q[6] = qb.z; q[7] = qb.w;
+    }
+    if constexpr (DT == ECF_F32) {
+      const uint4 rb = ldg_v4(reinterpret_cast<const char*>(M.W) + ((int64_t)row * M.ld + c0) * 4 + 16);
+      raw[0] = r.a.x; raw[1] = r.a.y; raw[2] = r.a.z; raw[3] = r.a.w; raw[4] = rb.x; raw[5] = rb.y; raw[6] = rb.z; raw[7] = rb.w;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[j] = __float_as_uint(wanda_score(__uint_as_float(raw[j]), q[j]));
+    } else {
+      raw[0] = r.a.x; raw[1] = r.a.y; raw[2] = r.a.z; raw[3] = r.a.w;
+      raw[4] = raw[5] = raw[6] = raw[7] = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float w0, w1;
+        unpack2<DT>(raw[j], w0, w1);
+        u[2 * j] = __float_as_uint(wanda_score(w0, q[2 * j]));
+        u[2 * j + 1] = __float_as_uint(wanda_score(w1, q[2 * j + 1]));
+      }
     }
   } else {
+    const char* wrow = reinterpret_cast<const char*>(M.W) + (int64_t)row * M.ld * DType<DT>::kBytes;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      if (c0 + j < C) {
-        if constexpr (DT == ECF_F32)
-          raw[j] = reinterpret_cast<const uint32_t*>(wrow)[c0 + j];
-        else
-          raw[j] = reinterpret_cast<const uint16_t*>(wrow)[c0 + j];
+      raw[j] = 0;
+      if (c0 + j < M.C) {
+        const float w = load_elem<DT>(wrow, c0 + j);
+        const float q = SQRT_INLINE ? __fadd_rn(sqrtf(M.s[c0 + j]), 0.f) : M.q[c0 + j];
+        u[j] = __float_as_uint(wanda_score(w, q)) & 0x7fffffffu;  // keep real scores apart from the padding pattern
       } else {
-        raw[j] = 0;
+        u[j] = 0xffffffffu;
       }
     }
   }
 }
 
-template <int DT>
-__device__ __forceinline__ float lt_to_float(uint32_t raw) {
-  if constexpr (DT == ECF_F32) return __uint_as_float(raw);
-  if constexpr (DT == ECF_BF16) return __uint_as_float(raw << 16);
-  return __half2float(__ushort_as_half((unsigned short)raw));
-}
-
-// keys of the 8 elements of vector `lv` of matrix M (out-of-range columns get key 0xffffffff: never counted)
-template <int DT, bool ALIGNED, bool SQRT_INLINE>
-__device__ __forceinline__ void lt_keys(const LtMat& M, int64_t lv, uint32_t (&key)[8], uint32_t (&raw)[8], int64_t& row, int64_t& c0) {
-  if (M.nvec < (1ll << 31)) {  // 32-bit division: every BASELINE.json matrix
-    const uint32_t r32 = (uint32_t)lv / (uint32_t)M.nvpr;
-    row = r32;
-    c0 = (int64_t)((uint32_t)lv - r32 * (uint32_t)M.nvpr) * 8;
-  } else {
-    row = lv / M.nvpr;
-    c0 = (lv - row * M.nvpr) * 8;
-  }
-  const char* wrow = reinterpret_cast<const char*>(M.W) + row * M.ld * DType<DT>::kBytes;
-  lt_load_chunk<DT, ALIGNED>(wrow, c0, M.C, raw);
-  float q[8];
-  if (!SQRT_INLINE && ALIGNED) {
-    const float4 qa = *reinterpret_cast<const float4*>(M.q + c0), qb = *reinterpret_cast<const float4*>(M.q + c0 + 4);
-    q[0] = qa.x; q[1] = qa.y; q[2] = qa.z; q[3] = qa.w; q[4] = qb.x; q[5] = qb.y; q[6] = qb.z; q[7] = qb.w;
-  } else {
+// upper 16 bits of the 8 scores, packed two per word, clamped to the finite fp16 patterns (padding -> +inf pattern)
+template <bool ALIGNED>
+__device__ __forceinline__ void lt_coarse(const uint32_t (&u)[8], uint32_t (&co)[4]) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (c0 + j < M.C) q[j] = SQRT_INLINE ? __fadd_rn(sqrtf(M.s[c0 + j]), 0.f) : M.q[c0 + j];
-      else q[j] = 0.f;
+  for (int j = 0; j < 4; ++j) {
+    uint32_t p = __vminu2(__byte_perm(u[2 * j], u[2 * j + 1], 0x7632) & 0x7fff7fffu, 0x7bff7bffu);
+    if constexpr (!ALIGNED) {
+      if (u[2 * j] == 0xffffffffu) p = (p & 0xffff0000u) | kLtTop;
+      if (u[2 * j + 1] == 0xffffffffu) p = (p & 0x0000ffffu) | (kLtTop << 16);
     }
+    co[j] = p;
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    key[j] = (c0 + j < M.C) ? score_key(wanda_score(lt_to_float<DT>(raw[j]), q[j])) : 0xffffffffu;
 }
 
-// dispatch a generic lambda on (dtype, aligned) of a matrix
+// dispatch a statement on (dtype, aligned) of a matrix
 #define LT_DISPATCH(M, CALL)                                                  \
   do {                                                                        \
     switch ((M).dtype * 2 + (M).aligned) {                                    \
@@ -148,6 +208,7 @@ __device__ __forceinline__ void lt_keys(const LtMat& M, int64_t lv, uint32_t (&k
 
 // per-matrix select state every CTA keeps (identical in all CTAs: derived from global memory after a barrier)
 struct LtSel {
+  uint32_t lo, hi;          // coarse bracket
   uint32_t lo32, range_hi;  // bracket as fp32 keys: [lo32, lo32 + range)  (range_hi: range - 1, fits 32 bits)
   int nd;                   // 11-bit digits needed for (key - lo32)
   uint32_t prefix;          // digits fixed so far (right aligned)
@@ -158,65 +219,246 @@ struct LtSel {
 
 __device__ __forceinline__ int lt_shift(int nd, int level) { return (nd - 1 - level) * 11; }
 
-// block-wide: find the bin of a 2 048-bin global histogram holding rank `rem`; returns bin, updates rem
-__device__ __forceinline__ uint32_t lt_find_bin(const unsigned* hist, unsigned long long& rem, unsigned long long* warp_tot /*[32] smem*/,
-                                                uint32_t* out /*[2] smem*/) {
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  constexpr int PER = kLtBins / kLtThreads;  // 4
-  unsigned long long mine[PER], sum = 0;
+// P3 main path for one vector: 16 x #(key < lo) via mask popcounts; returns non-zero when an element is in [lo, hi)
+template <int DT, bool AL>
+__device__ __forceinline__ uint32_t lt_count_vec(const LtMat& M, uint32_t row, uint32_t col, const LtRaw& r, __half2 pl, __half2 ph,
+                                                 int& pc16, uint32_t (&u)[8]) {
+  uint32_t raw[8], co[4];
+  lt_score_bits<DT, AL, false>(M, row, col, r, u, raw);
+  lt_coarse<AL>(u, co);
+  uint32_t x = 0;
 #pragma unroll
-  for (int j = 0; j < PER; ++j) {
-    mine[j] = __ldcg(hist + tid * PER + j);
-    sum += mine[j];
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t ml = __hlt2_mask(lt_h2(co[j]), pl), mh = __hlt2_mask(lt_h2(co[j]), ph);
+    x |= ml ^ mh;
+    pc16 += __popc(ml);
   }
+  return x;
+}
+
+// bracket elements of one vector -> digit histogram (level 0: every bracket element, counted in nb; level > 0: the
+// elements whose higher digits equal `prefix`)
+__device__ __forceinline__ void lt_hist_vec(const uint32_t (&u)[8], const LtSel& S, int level, unsigned* hist, unsigned& nb) {
+  const int sh = lt_shift(S.nd, level);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const uint32_t key = score_key(__uint_as_float(u[e]));
+    const uint32_t d = key - S.lo32;
+    if (u[e] != 0xffffffffu && key >= S.lo32 && d <= S.range_hi) {
+      if (level == 0) {
+        ++nb;
+        atomicAdd(hist + (d >> sh), 1u);
+      } else if ((d >> (sh + 11)) == S.prefix) {
+        atomicAdd(hist + ((d >> sh) & (kLtBins - 1)), 1u);
+      }
+    }
+  }
+}
+
+// P5 for one vector: zero the elements with score bits < tcmp
+template <int DT, bool AL>
+__device__ __forceinline__ void lt_apply_vec(const LtMat& M, uint32_t row, uint32_t col, const LtRaw& r, uint32_t tcmp, int& zeros) {
+  uint32_t u[8], raw[8];
+  lt_score_bits<DT, AL, false>(M, row, col, r, u, raw);
+  const int64_t c0 = (int64_t)col * 8;
+  char* wrow = reinterpret_cast<char*>(M.W) + (int64_t)row * M.ld * DType<DT>::kBytes;
+  uint32_t m = 0;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) m |= (u[e] < tcmp ? 1u : 0u) << e;  // padding / NaN patterns are never below tcmp
+  if constexpr (AL) {
+    if constexpr (DT == ECF_F32) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (m >> e & 1) raw[e] = 0;
+      if (m & 0x0fu) stg_v4(wrow + c0 * 4, make_uint4(raw[0], raw[1], raw[2], raw[3]));
+      if (m & 0xf0u) stg_v4(wrow + c0 * 4 + 16, make_uint4(raw[4], raw[5], raw[6], raw[7]));
+      if (M.n_zero != nullptr) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) zeros += (raw[e] & 0x7fffffffu) == 0 ? 1 : 0;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t keep = ((m >> (2 * j) & 1) ? 0u : 0x0000ffffu) | ((m >> (2 * j + 1) & 1) ? 0u : 0xffff0000u);
+        raw[j] &= keep;
+      }
+      if (m) stg_v4(wrow + c0 * 2, make_uint4(raw[0], raw[1], raw[2], raw[3]));
+      if (M.n_zero != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) zeros += ((raw[j] & 0x00007fffu) == 0 ? 1 : 0) + ((raw[j] & 0x7fff0000u) == 0 ? 1 : 0);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (c0 + e < M.C) {
+        const bool p = m >> e & 1;
+        if (p) store_zero<DT>(wrow, c0 + e);
+        if (M.n_zero != nullptr) zeros += (p || load_elem<DT>(wrow, c0 + e) == 0.f) ? 1 : 0;
+      }
+    }
+  }
+  if (M.mask != nullptr) M.mask[(int64_t)row * M.mask_ld + col] = (uint8_t)m;
+}
+
+// Grid-wide barrier for the co-resident (cooperative) grid.  cooperative_groups' grid.sync() funnels every CTA
+// through ONE counter -- ~300 same-address atomics serialise in the L2 for ~6 us on B200.  Here CTAs arrive on one of
+// ~sqrt(grid) group counters (distinct 128-byte lines), the last arrival of a group moves on to the top counter and
+// the last one there publishes the new generation, which everybody polls.  Counters reset themselves.
+__device__ __forceinline__ void lt_grid_barrier(unsigned* bar, unsigned& gen) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ++gen;
+    const unsigned nb = gridDim.x;
+    unsigned gs = 1;
+    while (gs * gs < nb) ++gs;
+    if ((nb + gs - 1) / gs > (unsigned)kLtBarMaxGroups) gs = (nb + kLtBarMaxGroups - 1) / kLtBarMaxGroups;
+    const unsigned ng = (nb + gs - 1) / gs;
+    const unsigned g = blockIdx.x / gs;
+    const unsigned members = min(gs, nb - g * gs);
+    __threadfence();
+    if (atomicAdd(bar + 32 * (1 + g), 1u) == members - 1) {
+      bar[32 * (1 + g)] = 0u;
+      __threadfence();
+      if (atomicAdd(bar + 1, 1u) == ng - 1) {
+        bar[1] = 0u;
+        __threadfence();
+        atomicExch(bar, gen);
+      }
+    }
+    while (*reinterpret_cast<volatile unsigned*>(bar) != gen) {}
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// One warp per matrix: find the bin of its 2 048-bin digit histogram (level `level`) that holds rank sel.rem.
+__device__ __forceinline__ void lt_find_bins(const LtBatch& b, LtSel* sel, int level) {
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (wid < b.n && sel[wid].nd > level) {
+    constexpr int PER = kLtBins / 32;  // 64 consecutive bins per lane
+    const uint4* my = reinterpret_cast<const uint4*>(b.m[wid].hist + level * kLtBins + lane * PER);
+    unsigned long long sum = 0;
+#pragma unroll 4
+    for (int j = 0; j < PER / 4; ++j) {
+      const uint4 v = __ldcg(my + j);
+      sum += (unsigned long long)v.x + v.y + v.z + v.w;
+    }
+    unsigned long long inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    const unsigned long long rem = sel[wid].rem;
+    unsigned long long run = inc - sum;
+    __syncwarp();
+    if (rem >= run && rem < run + sum) {  // exactly one lane
+      for (int j = 0; j < PER / 4; ++j) {
+        const uint4 v = __ldcg(my + j);
+        const unsigned cs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (rem >= run && rem < run + cs[e]) {
+            sel[wid].prefix = (sel[wid].prefix << 11) | (uint32_t)(lane * PER + 4 * j + e);
+            sel[wid].rem = rem - run;
+            sel[wid].done = level + 1;
+          }
+          run += cs[e];
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// P2: the calling CTA turns the sample histogram of matrix M into a coarse bracket (and cleans the histogram)
+__device__ __forceinline__ void lt_bracket(const LtMat& M, unsigned long long* sh_scan /*[36]*/) {
+  const int tid = threadIdx.x;
+  constexpr int PER = kLtCoarseBins / kLtThreads;  // 64 consecutive bins per thread, read as 16 independent 128-bit loads
+  const uint4* my_bins = reinterpret_cast<const uint4*>(M.coarse + tid * PER);
+  unsigned long long sum = 0;
+#pragma unroll 8
+  for (int j = 0; j < PER / 4; ++j) {
+    const uint4 v = __ldcg(my_bins + j);
+    sum += (unsigned long long)v.x + v.y + v.z + v.w;
+  }
+  const int lane = tid & 31, wid = tid >> 5;
   unsigned long long inc = sum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
     if (lane >= o) inc += t;
   }
-  if (lane == 31) warp_tot[wid] = inc;
+  if (lane == 31) sh_scan[wid] = inc;
   __syncthreads();
   if (wid == 0) {
-    unsigned long long w = lane < kLtThreads / 32 ? warp_tot[lane] : 0ull;
+    unsigned long long w = lane < kLtThreads / 32 ? sh_scan[lane] : 0ull;
     unsigned long long winc = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const unsigned long long t = __shfl_up_sync(0xffffffffu, winc, o);
       if (lane >= o) winc += t;
     }
-    if (lane < kLtThreads / 32) warp_tot[lane] = winc - w;  // exclusive
-  }
-  __syncthreads();
-  unsigned long long run = warp_tot[wid] + inc - sum;
-#pragma unroll
-  for (int j = 0; j < PER; ++j) {
-    if (rem >= run && rem < run + mine[j]) {
-      out[0] = (uint32_t)(tid * PER + j);
-      reinterpret_cast<unsigned long long*>(warp_tot)[33] = rem - run;
+    if (lane < kLtThreads / 32) sh_scan[lane] = winc - w;
+    if (lane == kLtThreads / 32 - 1) {
+      const unsigned long long ns = winc;  // total number of samples
+      const double numel = (double)M.R * (double)M.C;
+      const long long rs = (long long)((double)M.kth * (double)ns / numel);
+      const long long delta = M.sample_stride > 1 ? (long long)(2.5f * sqrtf((float)ns)) + 4 : 0;
+      reinterpret_cast<long long*>(sh_scan)[32] = rs - delta;
+      reinterpret_cast<long long*>(sh_scan)[33] = rs + delta;
+      M.bracket[0] = 0u;
+      M.bracket[1] = kLtTop;
+      M.cnt[0] = 0ull;
+      M.cnt[1] = 0ull;
     }
-    run += mine[j];
   }
   __syncthreads();
-  rem = reinterpret_cast<unsigned long long*>(warp_tot)[33];
-  const uint32_t bin = out[0];
+  const long long r_lo = reinterpret_cast<long long*>(sh_scan)[32], r_hi = reinterpret_cast<long long*>(sh_scan)[33];
+  unsigned long long run = sh_scan[wid] + inc - sum;  // samples in the bins before this thread's first bin
+  if (sum) {  // only threads whose bins hold samples can contain the two ranks
+#pragma unroll 4
+    for (int j = 0; j < PER / 4; ++j) {
+      const uint4 v = __ldcg(my_bins + j);
+      const unsigned cs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const unsigned long long c = cs[e];
+        const int bin = tid * PER + 4 * j + e;
+        if (c) {
+          if (r_lo >= 0 && (unsigned long long)r_lo >= run && (unsigned long long)r_lo < run + c) M.bracket[0] = (uint32_t)bin;
+          if (r_hi >= 0 && (unsigned long long)r_hi >= run && (unsigned long long)r_hi < run + c) M.bracket[1] = (uint32_t)bin + 1u;
+        }
+        run += c;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < PER / 4; ++j)  // self-cleaning for the next launch
+      reinterpret_cast<uint4*>(M.coarse + tid * PER)[j] = make_uint4(0, 0, 0, 0);
+  }
   __syncthreads();
-  return bin;
 }
 
 __global__ void __launch_bounds__(kLtThreads, 2) layer_thresh_batched_kernel(const __grid_constant__ LtBatch b) {
-  extern __shared__ unsigned sh_hist[];  // [n][kLtBins]
+  // dynamic shared memory: P1 uses it as the packed sample histogram; afterwards [n][kLtBins] digit histograms followed
+  // by the bracket-vector list
+  extern __shared__ unsigned sh_dyn[];
+  unsigned* sh_hist = sh_dyn;
+  uint32_t* sh_list = sh_dyn + b.n * kLtBins;
   __shared__ unsigned sh_cnt[kLtMaxMat][2];  // per-CTA counts fit 32 bits (a CTA sees < 2^32 elements)
   __shared__ unsigned long long sh_scan[36];
-  __shared__ uint32_t sh_out[2];
   __shared__ LtSel sel[kLtMaxMat];
-  const int tid = threadIdx.x;
+  __shared__ unsigned sh_list_n;
+  __shared__ int sh_overflow, sh_last;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int64_t gthreads = (int64_t)gridDim.x * kLtThreads;
   const int64_t gtid = (int64_t)blockIdx.x * kLtThreads + tid;
-  cg::grid_group grid = cg::this_grid();
+  const bool list_ok = b.total_vec < (1ll << 32);  // the list stores 32-bit flat vector indices
+  unsigned bar_gen = *reinterpret_cast<volatile unsigned*>(b.bar);  // read before this CTA's first arrival: nobody can have advanced it
   lt_stamp(b, 0);
 
-  // ================= P1: q tables + sample histogram of the upper 16 key bits ======================================
+  // ================= P1: q tables + per-CTA sample histograms of the upper 16 key bits -> global ===================
   for (int64_t i = gtid; i < (int64_t)b.n * 3 * kLtBins; i += gthreads) {  // digit histograms start from zero
     const int mi = (int)(i / (3 * kLtBins));
     b.m[mi].hist[i - (int64_t)mi * 3 * kLtBins] = 0u;
@@ -228,107 +470,82 @@ __global__ void __launch_bounds__(kLtThreads, 2) layer_thresh_batched_kernel(con
     const int64_t cc = c - M.col_begin;
     M.q[cc] = __fadd_rn(sqrtf(M.s[cc]), 0.f);
   }
-  for (int mi = 0; mi < b.n; ++mi) {
-    const LtMat& M = b.m[mi];
-    const int64_t nsv = (M.nvec + M.sample_stride - 1) / M.sample_stride;
-    for (int64_t j = gtid; j < nsv; j += gthreads) {
-      int64_t lv = j * M.sample_stride;
-      if (M.sample_stride > 1) lv += (int64_t)(((uint32_t)j * 2654435761u) >> 8) % M.sample_stride;
-      if (lv >= M.nvec) lv = M.nvec - 1;
-      uint32_t key[8], raw[8];
-      int64_t row, c0;
-      LT_DISPATCH(M, (lt_keys<DT, AL, true>(M, lv, key, raw, row, c0)));
+  {
+    // CTA c samples slice c / n of matrix c % n into a shared-memory histogram (16-bit counters, two per word) and
+    // adds its non-empty bins to the global one: ~300 global REDs per CTA instead of one per sample on a few hundred
+    // hot addresses.  The last CTA of a matrix (ticket) goes straight on to P2 for it: no grid barrier in between.
+    const int nslices = max(1, (int)gridDim.x / b.n);
+    const int mi = (int)blockIdx.x % b.n, slice = (int)blockIdx.x / b.n;
+    if (slice < nslices) {
+      const LtMat& M = b.m[mi];
+      const int64_t nsv = (M.nvec + M.sample_stride - 1) / M.sample_stride;
+      const int64_t per = (nsv + nslices - 1) / nslices;
+      const int64_t j0 = min(nsv, (int64_t)slice * per), j1 = min(nsv, j0 + per);
+      for (int64_t cb = j0; cb < j1; cb += kLtSampChunk) {
+        for (int i = tid; i < kLtSampWords; i += kLtThreads) sh_dyn[i] = 0u;
+        __syncthreads();
+        const int64_t ce = min(j1, cb + (int64_t)kLtSampChunk);
+        for (int64_t j = cb + tid; j < ce; j += kLtThreads) {
+          int64_t lv = j * M.sample_stride;
+          if (M.sample_stride > 1) lv += (int64_t)(((uint32_t)j * 2654435761u) >> 8) % M.sample_stride;
+          if (lv >= M.nvec) lv = M.nvec - 1;
+          LtCur cur;
+          cur.mi = mi;
+          lt_seek(b, M.vec_begin + lv, cur);
+          LtRaw r;
+          lt_issue(M, cur, r);
+          uint32_t u[8], raw[8];
+          LT_DISPATCH(M, (lt_score_bits<DT, AL, true>(M, cur.row, cur.col, r, u, raw)));
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (key[e] != 0xffffffffu) atomicAdd(M.coarse + (key[e] >> 16), 1u);
-    }
-  }
-  grid.sync();
-  lt_stamp(b, 1);
-
-  // ================= P2: one CTA per matrix turns the sample histogram into a coarse bracket ======================
-  if ((int)blockIdx.x < b.n) {
-    const LtMat& M = b.m[blockIdx.x];
-    constexpr int PER = kLtCoarseBins / kLtThreads;  // 64 consecutive bins per thread, read as 16 independent 128-bit loads
-    const uint4* my_bins = reinterpret_cast<const uint4*>(M.coarse + tid * PER);
-    unsigned long long sum = 0;
-    {
-      uint4 v[PER / 4];
-#pragma unroll
-      for (int j = 0; j < PER / 4; ++j) v[j] = __ldcg(my_bins + j);
-#pragma unroll
-      for (int j = 0; j < PER / 4; ++j) sum += (unsigned long long)v[j].x + v[j].y + v[j].z + v[j].w;
-    }
-    const int lane = tid & 31, wid = tid >> 5;
-    unsigned long long inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) sh_scan[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-      unsigned long long w = lane < kLtThreads / 32 ? sh_scan[lane] : 0ull;
-      unsigned long long winc = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, winc, o);
-        if (lane >= o) winc += t;
-      }
-      if (lane < kLtThreads / 32) sh_scan[lane] = winc - w;
-      if (lane == kLtThreads / 32 - 1) sh_scan[34] = winc;  // total number of samples
-    }
-    __syncthreads();
-    const unsigned long long ns = sh_scan[34];
-    const double numel = (double)M.R * (double)M.C;
-    const long long rs = (long long)((double)M.kth * (double)ns / numel);
-    const long long delta = M.sample_stride > 1 ? (long long)(2.5 * sqrt((double)ns)) + 4 : 0;
-    const long long r_lo = rs - delta, r_hi = rs + delta;
-    if (tid == 0) {
-      M.bracket[0] = 0u;
-      M.bracket[1] = 0x8000u;
-      M.bracket[2] = 0u;
-      M.cnt[0] = 0ull;
-      M.cnt[1] = 0ull;
-    }
-    __syncthreads();
-    unsigned long long run = sh_scan[wid] + inc - sum;  // samples in the bins before this thread's first bin
-    if (sum) {  // only threads whose bins hold samples can contain the two ranks
-#pragma unroll 4
-      for (int j = 0; j < PER / 4; ++j) {
-        const uint4 v = __ldcg(my_bins + j);
-        const unsigned cs[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const unsigned long long c = cs[e];
-          const int bin = tid * PER + 4 * j + e;
-          if (c) {
-            if (r_lo >= 0 && (unsigned long long)r_lo >= run && (unsigned long long)r_lo < run + c) M.bracket[0] = (uint32_t)bin;
-            if (r_hi >= 0 && (unsigned long long)r_hi >= run && (unsigned long long)r_hi < run + c) M.bracket[1] = (uint32_t)bin + 1u;
+          for (int e = 0; e < 8; ++e) {
+            if (u[e] != 0xffffffffu) {
+              const uint32_t bin = min(score_key(__uint_as_float(u[e])) >> 16, 0x7bffu);
+              atomicAdd(&sh_dyn[bin >> 1], 1u << ((bin & 1u) * 16));
+            }
           }
-          run += c;
         }
+        __syncthreads();
+        for (int i = tid; i < kLtSampWords; i += kLtThreads) {
+          const unsigned w = sh_dyn[i];
+          if (w & 0xffffu) atomicAdd(M.coarse + 2 * i, w & 0xffffu);
+          if (w >> 16) atomicAdd(M.coarse + 2 * i + 1, w >> 16);
+        }
+        __syncthreads();
       }
-#pragma unroll
-      for (int j = 0; j < PER / 4; ++j)  // self-cleaning for the next launch
-        reinterpret_cast<uint4*>(M.coarse + tid * PER)[j] = make_uint4(0, 0, 0, 0);
+      lt_stamp(b, 13);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        const unsigned prev = atomicAdd(M.bracket + 3, 1u);
+        sh_last = (prev == (unsigned)nslices - 1);
+        if (sh_last) M.bracket[3] = 0u;
+      }
+      __syncthreads();
+      if (sh_last) {
+        __threadfence();
+        lt_bracket(M, sh_scan);  // ================= P2 =================
+      }
     }
   }
-  grid.sync();
+  lt_stamp(b, 14);
+  lt_grid_barrier(b.bar, bar_gen);
+  lt_stamp(b, 1);
   lt_stamp(b, 2);
 
-  // ================= P3 (+ retry): #(key < lo) and the top-digit histogram of the bracket =========================
+  // ================= P3 (+ retry): #(key < lo), bracket vectors -> list -> top-digit histogram ====================
   for (int mi = tid; mi < b.n; mi += kLtThreads) sel[mi].active = 1;
   __syncthreads();
-  for (int round = 0;; ++round) {
+  int rounds = 0;
+  for (;; ++rounds) {
     for (int mi = tid; mi < b.n; mi += kLtThreads) {
       const LtMat& M = b.m[mi];
       if (sel[mi].active) {
         const uint32_t lo = __ldcg(M.bracket), hi = __ldcg(M.bracket + 1);
         const uint32_t lo32 = lo << 16;
-        const uint32_t range_hi = (hi >= 0x8000u ? 0x80000000u : (hi << 16)) - lo32 - 1u;
+        const uint32_t range_hi = (hi >= kLtTop ? 0x80000000u : (hi << 16)) - lo32 - 1u;
         const int bits = 32 - __clz(range_hi | 1u);
+        sel[mi].lo = lo;
+        sel[mi].hi = hi;
         sel[mi].lo32 = lo32;
         sel[mi].range_hi = range_hi;
         sel[mi].nd = (bits + 10) / 11;
@@ -339,44 +556,87 @@ __global__ void __launch_bounds__(kLtThreads, 2) layer_thresh_batched_kernel(con
       sh_cnt[mi][1] = 0u;
     }
     for (int i = tid; i < b.n * kLtBins; i += kLtThreads) sh_hist[i] = 0;
-    __syncthreads();
-    {
-      int mi = 0;
-      unsigned c_lt = 0, c_band = 0;
-      for (int64_t v = gtid; v < b.total_vec; v += gthreads) {
-        if (v >= b.m[mi].vec_begin + b.m[mi].nvec) {
-          if (c_lt) atomicAdd(&sh_cnt[mi][0], c_lt);
-          if (c_band) atomicAdd(&sh_cnt[mi][1], c_band);
-          c_lt = c_band = 0;
-          while (v >= b.m[mi].vec_begin + b.m[mi].nvec) ++mi;
-        }
-        if (!sel[mi].active) continue;
-        const LtMat& M = b.m[mi];
-        uint32_t key[8], raw[8];
-        int64_t row, c0;
-        LT_DISPATCH(M, (lt_keys<DT, AL, false>(M, v - M.vec_begin, key, raw, row, c0)));
-        const uint32_t lo32 = sel[mi].lo32, rh = sel[mi].range_hi;
-        const int sh = lt_shift(sel[mi].nd, 0);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const uint32_t d = key[e] - lo32;
-          c_lt += key[e] < lo32 ? 1u : 0u;  // padding keys (0xffffffff) are never below lo32
-          if (key[e] >= lo32 && d <= rh) {
-            ++c_band;
-            atomicAdd(&sh_hist[mi * kLtBins + (d >> sh)], 1u);
-          }
-        }
-      }
-      // one shared atomic per warp when all its lanes ended in the same matrix (the common case)
-      if (__all_sync(0xffffffffu, mi == __shfl_sync(0xffffffffu, mi, 0))) {
-        c_lt = (unsigned)warp_sum((int)c_lt);
-        c_band = (unsigned)warp_sum((int)c_band);
-        if ((tid & 31) != 0) c_lt = c_band = 0;
-      }
-      if (c_lt) atomicAdd(&sh_cnt[mi][0], c_lt);
-      if (c_band) atomicAdd(&sh_cnt[mi][1], c_band);
+    if (tid == 0) {
+      sh_list_n = 0u;
+      sh_overflow = 0;
     }
     __syncthreads();
+    {
+      LtCur cur, nxt;
+      LtRaw ra, rb;
+      cur.mi = 0;
+      int cmi = -1;  // matrix the running counter and the pivots belong to
+      int pc16 = 0;
+      __half2 pl = lt_h2(0u), ph = lt_h2(0u);
+      int64_t v = gtid;
+      if (v < b.total_vec) {
+        lt_seek(b, v, cur);
+        if (sel[cur.mi].active) lt_issue(b.m[cur.mi], cur, ra);
+      }
+      for (int64_t base = gtid - lane; base < b.total_vec; base += gthreads, v += gthreads) {  // warp-uniform trip count
+        bool cand = false;
+        uint32_t u[8];
+        if (v < b.total_vec) {
+          // the next vector's load goes out before this one is processed: two 16-byte requests in flight per thread
+          nxt = cur;
+          lt_next(b, v + gthreads, nxt);
+          if (v + gthreads < b.total_vec && sel[nxt.mi].active) lt_issue(b.m[nxt.mi], nxt, rb);
+          if (cur.mi != cmi) {
+            if (pc16) atomicAdd(&sh_cnt[cmi][0], (unsigned)pc16 >> 4);
+            pc16 = 0;
+            cmi = cur.mi;
+            pl = lt_h2(lt_dup(sel[cmi].lo));
+            ph = lt_h2(lt_dup(sel[cmi].hi));
+          }
+          if (sel[cmi].active) {
+            const LtMat& M = b.m[cmi];
+            uint32_t x = 0;
+            LT_DISPATCH(M, (x = lt_count_vec<DT, AL>(M, cur.row, cur.col, ra, pl, ph, pc16, u)));
+            cand = x != 0;
+          }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, cand);
+        if (bal) {
+          unsigned pos = 0;
+          if (lane == 0) pos = atomicAdd(&sh_list_n, (unsigned)__popc(bal));
+          pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << lane) - 1u));
+          if (cand) {
+            if (list_ok && pos < (unsigned)kLtListCap) {
+              sh_list[pos] = (uint32_t)v;
+            } else {  // list full: histogram this vector on the spot; later digits re-scan this CTA's share of W
+              sh_overflow = 1;
+              unsigned nb = 0;
+              lt_hist_vec(u, sel[cmi], 0, sh_hist + cmi * kLtBins, nb);
+              if (nb) atomicAdd(&sh_cnt[cmi][1], nb);
+            }
+          }
+        }
+        cur = nxt;
+        ra = rb;
+      }
+      if (pc16) atomicAdd(&sh_cnt[cmi][0], (unsigned)pc16 >> 4);
+    }
+    __syncthreads();
+    lt_stamp(b, 6);
+    {
+      // walk the list: every lane has a bracket vector (re-read: L1/L2 hit), exact keys, top digit
+      const int n_list = list_ok ? (int)min(sh_list_n, (unsigned)kLtListCap) : 0;
+      LtCur cur;
+      for (int i = tid; i < n_list; i += kLtThreads) {
+        cur.mi = 0;
+        lt_seek(b, (int64_t)sh_list[i], cur);
+        const LtMat& M = b.m[cur.mi];
+        LtRaw r;
+        lt_issue(M, cur, r);
+        uint32_t u[8], raw[8];
+        LT_DISPATCH(M, (lt_score_bits<DT, AL, false>(M, cur.row, cur.col, r, u, raw)));
+        unsigned nb = 0;
+        lt_hist_vec(u, sel[cur.mi], 0, sh_hist + cur.mi * kLtBins, nb);
+        if (nb) atomicAdd(&sh_cnt[cur.mi][1], nb);
+      }
+    }
+    __syncthreads();
+    lt_stamp(b, 7);
     for (int i = tid; i < b.n * kLtBins; i += kLtThreads) {
       const unsigned c = sh_hist[i];
       const int mi = i / kLtBins;
@@ -386,17 +646,20 @@ __global__ void __launch_bounds__(kLtThreads, 2) layer_thresh_batched_kernel(con
       const unsigned long long c = sh_cnt[tid >> 1][tid & 1];
       if (c) atomicAdd(b.m[tid >> 1].cnt + (tid & 1), c);  // 64-bit global atomic: native
     }
-    grid.sync();
+    __syncthreads();
+    lt_stamp(b, 8);
+    lt_grid_barrier(b.bar, bar_gen);
     // every CTA checks the brackets (same global values everywhere)
     int any_retry = 0;
     for (int mi = 0; mi < b.n; ++mi) {
       const LtMat& M = b.m[mi];
       const unsigned long long c_lo = __ldcg(M.cnt), c_band = __ldcg(M.cnt + 1);
       const unsigned long long kth = (unsigned long long)M.kth;
-      const bool ok = kth >= c_lo && kth < c_lo + c_band;
+      const bool was_active = sel[mi].active != 0;
+      const bool ok = !was_active || (kth >= c_lo && kth < c_lo + c_band);
       if (!ok) any_retry = 1;
       __syncthreads();
-      if (tid == 0) {
+      if (tid == 0 && was_active) {
         sel[mi].active = ok ? 0 : 1;
         if (ok) sel[mi].rem = kth - c_lo;
       }
@@ -404,7 +667,7 @@ __global__ void __launch_bounds__(kLtThreads, 2) layer_thresh_batched_kernel(con
     __syncthreads();
     if (!any_retry) break;
     // rare: the k-th score is outside the sampled bracket.  Move to the side that holds it and count again.
-    grid.sync();  // everybody has read cnt / bracket
+    lt_grid_barrier(b.bar, bar_gen);  // everybody has read cnt / bracket
     if (blockIdx.x == 0) {
       for (int mi = 0; mi < b.n; ++mi) {
         if (!sel[mi].active) continue;
@@ -412,120 +675,110 @@ __global__ void __launch_bounds__(kLtThreads, 2) layer_thresh_batched_kernel(con
         if (tid == 0) {
           const uint32_t lo = M.bracket[0], hi = M.bracket[1];
           if ((unsigned long long)M.kth < M.cnt[0]) { M.bracket[0] = 0u; M.bracket[1] = lo; }
-          else { M.bracket[0] = hi; M.bracket[1] = 0x8000u; }
+          else { M.bracket[0] = hi; M.bracket[1] = kLtTop; }
           M.cnt[0] = 0ull;
           M.cnt[1] = 0ull;
         }
         for (int i = tid; i < kLtBins; i += kLtThreads) M.hist[i] = 0u;
       }
     }
-    grid.sync();
+    lt_grid_barrier(b.bar, bar_gen);
   }
 
   lt_stamp(b, 3);
   // ================= P4: resolve the digits (level 0 histogram is already in global memory) =======================
+  // NB a retry round only re-lists the matrices that were still active, so after a retry the list no longer covers
+  // the others: their later digits come from the re-scan path as well.
   int max_nd = 1;
   for (int mi = 0; mi < b.n; ++mi) max_nd = max(max_nd, sel[mi].nd);
   for (int level = 0; level < max_nd; ++level) {
-    // scan level `level` (every CTA computes the same bins)
-    for (int mi = 0; mi < b.n; ++mi) {
-      if (sel[mi].nd <= level) continue;
-      unsigned long long rem = sel[mi].rem;
-      const uint32_t bin = lt_find_bin(b.m[mi].hist + level * kLtBins, rem, sh_scan, sh_out);
-      if (tid == 0) {
-        sel[mi].prefix = (sel[mi].prefix << 11) | bin;
-        sel[mi].rem = rem;
-        sel[mi].done = level + 1;
-      }
-      __syncthreads();
-    }
+    lt_find_bins(b, sel, level);  // every CTA computes the same bins
+    lt_stamp(b, 9 + 3 * (level > 0 ? 1 : 0));
     if (level + 1 >= max_nd) break;
-    // histogram of the next digit for the elements matching the prefix (W is L2 resident by now)
+    // histogram of the next digit for the elements matching the prefix
     for (int i = tid; i < b.n * kLtBins; i += kLtThreads) sh_hist[i] = 0;
     __syncthreads();
-    {
-      int mi = 0;
-      for (int64_t v = gtid; v < b.total_vec; v += gthreads) {
-        while (v >= b.m[mi].vec_begin + b.m[mi].nvec) ++mi;
-        if (sel[mi].nd <= level + 1) continue;
-        const LtMat& M = b.m[mi];
-        uint32_t key[8], raw[8];
-        int64_t row, c0;
-        LT_DISPATCH(M, (lt_keys<DT, AL, false>(M, v - M.vec_begin, key, raw, row, c0)));
-        const uint32_t lo32 = sel[mi].lo32, rh = sel[mi].range_hi, prefix = sel[mi].prefix;
-        const int sh_prev = lt_shift(sel[mi].nd, level), sh = lt_shift(sel[mi].nd, level + 1);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const uint32_t d = key[e] - lo32;
-          if (key[e] >= lo32 && d <= rh && (d >> sh_prev) == prefix) atomicAdd(&sh_hist[mi * kLtBins + ((d >> sh) & (kLtBins - 1))], 1u);
+    if (sh_overflow || !list_ok || rounds > 0) {
+      LtCur cur;
+      cur.mi = 0;
+      int64_t v = gtid;
+      if (v < b.total_vec) lt_seek(b, v, cur);
+      for (; v < b.total_vec; v += gthreads) {
+        if (sel[cur.mi].nd > level + 1) {
+          const LtMat& M = b.m[cur.mi];
+          LtRaw r;
+          lt_issue(M, cur, r);
+          uint32_t u[8], raw[8];
+          LT_DISPATCH(M, (lt_score_bits<DT, AL, false>(M, cur.row, cur.col, r, u, raw)));
+          unsigned nb = 0;
+          lt_hist_vec(u, sel[cur.mi], level + 1, sh_hist + cur.mi * kLtBins, nb);
         }
+        lt_next(b, v + gthreads, cur);
+      }
+    } else {
+      const int n_list = (int)min(sh_list_n, (unsigned)kLtListCap);
+      LtCur cur;
+      for (int i = tid; i < n_list; i += kLtThreads) {
+        cur.mi = 0;
+        lt_seek(b, (int64_t)sh_list[i], cur);
+        if (sel[cur.mi].nd <= level + 1) continue;
+        const LtMat& M = b.m[cur.mi];
+        LtRaw r;
+        lt_issue(M, cur, r);
+        uint32_t u[8], raw[8];
+        LT_DISPATCH(M, (lt_score_bits<DT, AL, false>(M, cur.row, cur.col, r, u, raw)));
+        unsigned nb = 0;
+        lt_hist_vec(u, sel[cur.mi], level + 1, sh_hist + cur.mi * kLtBins, nb);
       }
     }
     __syncthreads();
+    lt_stamp(b, 10);
     for (int i = tid; i < b.n * kLtBins; i += kLtThreads) {
       const unsigned c = sh_hist[i];
       const int mi = i / kLtBins;
       if (c) atomicAdd(b.m[mi].hist + (level + 1) * kLtBins + (i - mi * kLtBins), c);
     }
-    grid.sync();
+    __syncthreads();
+    lt_stamp(b, 11);
+    lt_grid_barrier(b.bar, bar_gen);
   }
 
   lt_stamp(b, 4);
   // ================= P5: apply  score <= thres  in place ===========================================================
+  for (int mi = tid; mi < b.n; mi += kLtThreads) sh_cnt[mi][0] = 0u;
+  __syncthreads();
   {
-    int mi = 0;
+    LtCur cur, nxt;
+    LtRaw ra, rb;
+    cur.mi = 0;
+    int cmi = -1;
     int zeros = 0;
-    for (int64_t v = gtid; v < b.total_vec; v += gthreads) {
-      if (v >= b.m[mi].vec_begin + b.m[mi].nvec) {
-        if (b.m[mi].n_zero != nullptr && zeros) atomicAdd(b.m[mi].n_zero, (unsigned long long)zeros);
+    uint32_t tcmp = 0;
+    int64_t v = gtid;
+    if (v < b.total_vec) {
+      lt_seek(b, v, cur);
+      lt_issue(b.m[cur.mi], cur, ra);
+    }
+    for (; v < b.total_vec; v += gthreads) {
+      nxt = cur;
+      lt_next(b, v + gthreads, nxt);
+      if (v + gthreads < b.total_vec) lt_issue(b.m[nxt.mi], nxt, rb);
+      if (cur.mi != cmi) {
+        if (zeros) atomicAdd(&sh_cnt[cmi][0], (unsigned)zeros);
         zeros = 0;
-        while (v >= b.m[mi].vec_begin + b.m[mi].nvec) ++mi;
+        cmi = cur.mi;
+        const uint32_t tkey = sel[cmi].lo32 + sel[cmi].prefix;
+        // float semantics of `W_metric <= thres`: NaN scores are never pruned, a NaN threshold prunes nothing
+        tcmp = tkey > 0x7f800000u ? 0u : tkey + 1u;  // prune iff key < tcmp
       }
-      const LtMat& M = b.m[mi];
-      const uint32_t tkey = sel[mi].lo32 + sel[mi].prefix;
-      // float semantics of `W_metric <= thres`: NaN scores are never pruned, a NaN threshold prunes nothing
-      const uint32_t tcmp = tkey > 0x7f800000u ? 0u : tkey + 1u;  // prune iff key < tcmp
-      uint32_t key[8], raw[8];
-      int64_t row, c0;
-      LT_DISPATCH(M, (lt_keys<DT, AL, false>(M, v - M.vec_begin, key, raw, row, c0)));
-      uint32_t m = 0;
-      const uint32_t absmask = M.dtype == ECF_F32 ? 0x7fffffffu : 0x7fffu;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const bool p = key[e] < tcmp;
-        m |= (p ? 1u : 0u) << e;
-        if (p) raw[e] = 0;
-        zeros += (c0 + e < M.C && (raw[e] & absmask) == 0) ? 1 : 0;
-      }
-      char* wrow = reinterpret_cast<char*>(M.W) + row * M.ld * dtype_bytes(M.dtype);
-      if (m) {
-        if (M.aligned) {
-          if (M.dtype == ECF_F32) {
-            stg_v4(wrow + c0 * 4, make_uint4(raw[0], raw[1], raw[2], raw[3]));
-            stg_v4(wrow + c0 * 4 + 16, make_uint4(raw[4], raw[5], raw[6], raw[7]));
-          } else {
-            stg_v4(wrow + c0 * 2, make_uint4(raw[0] | raw[1] << 16, raw[2] | raw[3] << 16, raw[4] | raw[5] << 16, raw[6] | raw[7] << 16));
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            if (c0 + e < M.C && (m >> e & 1)) {
-              if (M.dtype == ECF_F32) reinterpret_cast<float*>(wrow)[c0 + e] = 0.f;
-              else reinterpret_cast<uint16_t*>(wrow)[c0 + e] = 0;
-            }
-          }
-        }
-      }
-      if (M.mask != nullptr) M.mask[row * M.mask_ld + (c0 >> 3)] = (uint8_t)m;
+      const LtMat& M = b.m[cmi];
+      LT_DISPATCH(M, (lt_apply_vec<DT, AL>(M, cur.row, cur.col, ra, tcmp, zeros)));
+      cur = nxt;
+      ra = rb;
     }
-    // final flush: one atomic per warp when all its lanes ended in the same matrix (the common case)
-    const bool uni = __all_sync(0xffffffffu, mi == __shfl_sync(0xffffffffu, mi, 0));
-    if (uni) {
-      const int z = warp_sum(zeros);
-      if ((tid & 31) == 0 && z && b.m[mi].n_zero != nullptr) atomicAdd(b.m[mi].n_zero, (unsigned long long)z);
-    } else if (b.m[mi].n_zero != nullptr && zeros) {
-      atomicAdd(b.m[mi].n_zero, (unsigned long long)zeros);
-    }
+    if (zeros) atomicAdd(&sh_cnt[cmi][0], (unsigned)zeros);
+    __syncthreads();
+    if (tid < b.n && sh_cnt[tid][0] && b.m[tid].n_zero != nullptr) atomicAdd(b.m[tid].n_zero, (unsigned long long)sh_cnt[tid][0]);
   }
   lt_stamp(b, 5);
   if (blockIdx.x == 0) {
@@ -542,7 +795,7 @@ static size_t lt_mat_fixed_bytes() {
 
 size_t layer_thresh_batched_workspace_bytes(const ecf_layer_desc* descs, int n) {
   if (descs == nullptr || n < 1 || n > kLtMaxMat) return 0;
-  size_t total = 256;
+  size_t total = kLtHeaderBytes;
   for (int i = 0; i < n; ++i) {
     if (descs[i].C <= 0) return 0;
     total += lt_mat_fixed_bytes() + align_up((size_t)descs[i].C * sizeof(float), 256);
@@ -552,7 +805,7 @@ size_t layer_thresh_batched_workspace_bytes(const ecf_layer_desc* descs, int n) 
 
 size_t layer_thresh_workspace_bytes(int64_t R, int64_t C) {
   (void)R;
-  return 256 + lt_mat_fixed_bytes() + align_up((size_t)(C > 0 ? C : 1) * sizeof(float), 256);
+  return kLtHeaderBytes + lt_mat_fixed_bytes() + align_up((size_t)(C > 0 ? C : 1) * sizeof(float), 256);
 }
 
 }  // namespace ecf
@@ -573,6 +826,7 @@ extern "C" int ecf_wanda_layer_thresh_apply_batched(const ecf_layer_desc* descs,
     ECF_REQUIRE(d.R > 0 && d.C > 0 && d.ld >= d.C, ECF_ERR_INVALID, "layer_thresh: bad shape R=%lld C=%lld ld=%lld (matrix %d)",
                 (long long)d.R, (long long)d.C, (long long)d.ld, i);
     ECF_REQUIRE(d.dtype >= 0 && d.dtype <= 2, ECF_ERR_INVALID, "layer_thresh: unknown dtype %d (matrix %d)", d.dtype, i);
+    ECF_REQUIRE(d.R < (1ll << 31) && d.C < (1ll << 31), ECF_ERR_INVALID, "layer_thresh: R or C beyond 2^31 (matrix %d)", i);
     // python indexing: sort(...)[idx] raises IndexError for idx >= numel; negative idx is never produced
     ECF_REQUIRE(d.kth_index >= 0 && d.kth_index < d.R * d.C, ECF_ERR_RANGE,
                 "layer_thresh: kth_index %lld out of range for %lld elements (the reference raises IndexError)",
@@ -588,7 +842,9 @@ extern "C" int ecf_wanda_layer_thresh_apply_batched(const ecf_layer_desc* descs,
   b.n = n;
   char* p = reinterpret_cast<char*>(ws);
   b.stamps = reinterpret_cast<unsigned long long*>(p);
-  p += 256;
+  b.bar = reinterpret_cast<unsigned*>(p + 128);  // 128 bytes of stamps, then (1 + kLtBarMaxGroups) 128-byte barrier lines
+  static_assert(128 + (1 + kLtBarMaxGroups) * 128 <= kLtHeaderBytes, "workspace header too small");
+  p += kLtHeaderBytes;
   int64_t vec = 0, cols = 0;
   for (int i = 0; i < n; ++i) {
     const ecf_layer_desc& d = descs[i];
@@ -613,8 +869,16 @@ extern "C" int ecf_wanda_layer_thresh_apply_batched(const ecf_layer_desc* descs,
   }
   b.total_vec = vec;
   b.total_cols = cols;
+  int64_t samples = 0;
+  for (int i = 0; i < n; ++i) {
+    LtMat& M = b.m[i];
+    M.sample_begin = samples;
+    samples += (M.nvec + M.sample_stride - 1) / M.sample_stride;
+  }
+  b.total_samples = samples;
 
-  const size_t smem = (size_t)n * kLtBins * sizeof(unsigned);
+  size_t smem = (size_t)n * kLtBins * sizeof(unsigned) + (size_t)kLtListCap * sizeof(uint32_t);
+  if (smem < (size_t)kLtSampWords * sizeof(unsigned)) smem = (size_t)kLtSampWords * sizeof(unsigned);
   static size_t smem_opted = 0;
   if (smem > smem_opted) {
     ECF_CUDA_OK(cudaFuncSetAttribute(layer_thresh_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -627,6 +891,11 @@ extern "C" int ecf_wanda_layer_thresh_apply_batched(const ecf_layer_desc* descs,
   const int64_t cap = (int64_t)sm_count() * occ;
   if (want > cap) want = cap;
   if (want < n) want = n;  // P2 needs one CTA per matrix (n <= 8 <= SM count)
+  const int64_t gthreads = want * kLtThreads;
+  for (int i = 0; i < n; ++i) {
+    b.m[i].step_rows = gthreads / b.m[i].nvpr;
+    b.m[i].step_cols = gthreads % b.m[i].nvpr;
+  }
   void* args[] = {(void*)&b};
   ECF_CUDA_OK(cudaLaunchCooperativeKernel((const void*)layer_thresh_batched_kernel, dim3((unsigned)want), dim3(kLtThreads), args, smem,
                                           reinterpret_cast<cudaStream_t>(stream)));

@@ -186,6 +186,14 @@ def layer_thresh_phase_times_us(device) -> list:
     return [(b - a) / 1e3 for a, b in zip(t[:-1], t[1:])]
 
 
+def layer_thresh_stamps_us(device) -> list:
+    """Profiling aid: all 16 %globaltimer stamps of CTA 0 (us, relative to the kernel start; 0 = not taken)."""
+    torch.cuda.synchronize(device)
+    ws = _ws.get(device, 256, "layer_thresh")
+    t = ws[:128].view(torch.int64).tolist()
+    return [round((x - t[0]) / 1e3, 1) if x else 0 for x in t]
+
+
 def zo_perturb(W: torch.Tensor, z: torch.Tensor, scaling: float, eps: float) -> None:
     """W = rn(W + rn(rn(scaling*z)*eps)) in W's dtype, in place (A11)."""
     _require_cuda(W, z)

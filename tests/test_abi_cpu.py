@@ -64,7 +64,10 @@ def test_workspace_queries_are_pure_host_functions():
     d = (_abi.SqnormDesc * 2)()
     for i in range(2):
         d[i].x, d[i].scaler_row, d[i].T, d[i].C, d[i].ld, d[i].dtype = 4096, 8192 + 64 * i, 512, 2048, 2048, 2
-    assert lib.ecf_sqnorm_batched_workspace_bytes(d, 2) > lib.ecf_sqnorm_batched_workspace_bytes(d, 1) > 0
+    # two hooks on the SAME input (q/k share x) are computed once: no extra partial rows
+    assert lib.ecf_sqnorm_batched_workspace_bytes(d, 2) == lib.ecf_sqnorm_batched_workspace_bytes(d, 1) > 65536
+    d[1].x = 4096 + (1 << 22)
+    assert lib.ecf_sqnorm_batched_workspace_bytes(d, 2) > lib.ecf_sqnorm_batched_workspace_bytes(d, 1)
     assert lib.ecf_sqnorm_batched_workspace_bytes(d, 0) == 0
 
 

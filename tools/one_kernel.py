@@ -25,6 +25,8 @@ if which == "layer_block":
         torch.cuda.synchronize()
         print("block select ms", e0.elapsed_time(e1), "phase us (sample, bracket, count, refine, apply):",
               [round(x, 1) for x in ops.layer_thresh_phase_times_us(dev)])
+        print("   stamps us [start, P1+P2 end, =, P3 end, P4 end, P5 end, P3 loop, P3 walk, P3 flush, find0, walk1, flush1, find1, P1 sampled, P1 done]:",
+              ops.layer_thresh_stamps_us(dev)[:15])
 elif which in ("sqnorm_vit", "sqnorm_t5"):
     # the batched norm launch of one block forward at BLIP-2 shapes (R, C, dtype arguments are ignored)
     if which == "sqnorm_vit":

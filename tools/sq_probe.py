@@ -1,0 +1,48 @@
+"""Device timing of the batched norm launch at the BLIP-2 block-sweep shapes (16 calibration batches of 8)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from ecoflap_b200 import ops
+
+dev = torch.device("cuda", 0)
+PEAK = 6532.5
+f32, f16, bf16 = torch.float32, torch.float16, torch.bfloat16
+NB = 16
+CASES = {
+    # name: list of (T, C, dtype, number of Linears hooked on this input)
+    "vitg_block": [(2056, 1408, f32, 1), (2056, 1408, f16, 1), (2056, 1408, f32, 1), (2056, 6144, f16, 1)],
+    "t5_enc_block": [(512, 2048, bf16, 3), (512, 2048, bf16, 1), (512, 2048, bf16, 2), (512, 5120, bf16, 1)],
+    "t5_dec_block": [(256, 2048, bf16, 3), (256, 2048, bf16, 1), (256, 2048, bf16, 1), (512, 2048, bf16, 2),
+                     (256, 2048, bf16, 1), (256, 2048, bf16, 2), (256, 5120, bf16, 1)],
+    "llama_qkv": [(16384, 4096, f16, 3)],
+    "single_T5": [(512, 2048, bf16, 1)],
+    "big": [(131072, 4096, f16, 1)],
+}
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+for name, spec in CASES.items():
+    nb = 1 if name in ("single_T5", "big") else (8 if name == "llama_qkv" else NB)
+    items, alg, distinct = [], 0, 0
+    for (T, C, dt, nlin) in spec:
+        xs = [torch.randn(T, C, device=dev).to(dt) for _ in range(nb)]
+        distinct += nb * T * C * xs[0].element_size()
+        for _ in range(nlin):
+            s = torch.zeros(C, device=dev)
+            for j, x in enumerate(xs):
+                items.append((x, s, j / (j + 1.0), 1.0 / (8 * (j + 1))))
+                alg += T * C * x.element_size() + 8 * C
+    for _ in range(3):
+        ops.sqnorm_accum_batched(items)
+    torch.cuda.synchronize()
+    # the launch is replayed from a CUDA graph so that the host-side descriptor marshalling is not in the timing
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        ops.sqnorm_accum_batched(items)
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); graph.replay(); e1.record()
+        torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    print(f"{name:14s} {ms*1e3:8.1f} us  alg {alg/ms/1e6:7.0f} GB/s ({alg/ms/1e6/PEAK:.2f})  distinct {distinct/ms/1e6:7.0f} GB/s ({distinct/ms/1e6/PEAK:.2f})  MB {distinct/1e6:.0f}", flush=True)
+    del items
