@@ -280,19 +280,14 @@ def run_b200(args):
                 continue
             if layer_items:  # the per-layer selects of a block: one cooperative launch
                 ops.wanda_layer_thresh_apply_batched(layer_items)
-            rows = [(o, acc) for o, acc in zip(pb, accs) if o.spec.select == "row"]
-            for i, (o, acc) in enumerate(rows):
-                st = side[i]
-                st.wait_stream(main)
-                with torch.cuda.stream(st):
-                    ops.wanda_row_select_apply(o.W, acc.scaler_row, o.k)
-            for i in range(len(rows)):
-                main.wait_stream(side[i])
+            rows = [(o.W, acc.scaler_row, o.k) for o, acc in zip(pb, accs) if o.spec.select == "row"]
+            if rows:  # the per-row selects of a block: one persistent launch per distinct (row length, dtype)
+                ops.wanda_row_select_apply_batched(rows)
 
     launches_per_step = 0
     for pb in lins:
         launches_per_step += -(-(N_BATCHES * len(pb)) // _abi.SQNORM_MAX_BATCH)  # batched norm launches per block
-        launches_per_step += sum(1 for o in pb if o.spec.select == "row")
+        launches_per_step += len({(o.W.shape[1], o.W.dtype) for o in pb if o.spec.select == "row"})
         launches_per_step += 1 if any(o.spec.select == "layer" for o in pb) else 0  # batched cooperative select
 
     def barrier():
@@ -399,14 +394,14 @@ def run_b200(args):
             fam["layer_thresh"][0] += ms
             fam["layer_thresh"][1] += sum(wl.select_bytes(o.spec) for o, _ in layer)
             fam["layer_thresh"][2] += 1
-        for o, acc in zip(pb, accs):
-            if o.spec.select != "row":
-                continue
-            ms = timed_graph(lambda o=o, acc=acc: ops.wanda_row_select_apply(o.W, acc.scaler_row, o.k),
-                             prepare=lambda o=o: o.W.copy_(o.W0))
+        rows = [(o, acc) for o, acc in zip(pb, accs) if o.spec.select == "row"]
+        if rows:
+            items_r = [(o.W, acc.scaler_row, o.k) for o, acc in rows]
+            ms = timed_graph(lambda: ops.wanda_row_select_apply_batched(items_r),
+                             prepare=lambda: [o.W.copy_(o.W0) for o, _ in rows])
             fam["row_select"][0] += ms
-            fam["row_select"][1] += wl.select_bytes(o.spec)
-            fam["row_select"][2] += 1
+            fam["row_select"][1] += sum(wl.select_bytes(o.spec) for o, _ in rows)
+            fam["row_select"][2] += len({(o.W.shape[1], o.W.dtype) for o, _ in rows})
     del scratch
     kernels = {}
     for name, (ms, nbytes, n) in fam.items():

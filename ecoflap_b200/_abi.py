@@ -19,7 +19,7 @@ ERR_INVALID, ERR_WORKSPACE, ERR_CUDA, ERR_NO_DEVICE, ERR_RANGE = -1, -2, -3, -4,
 EXPORTED = (
     "ecf_version", "ecf_last_error", "ecf_device_sm_count", "ecf_workspace_bytes", "ecf_sqnorm_accum",
     "ecf_sqnorm_batched_workspace_bytes", "ecf_sqnorm_accum_batched",
-    "ecf_wanda_row_select_apply", "ecf_wanda_layer_thresh_apply",
+    "ecf_wanda_row_select_apply", "ecf_wanda_row_select_apply_batched", "ecf_wanda_layer_thresh_apply",
     "ecf_layer_thresh_batched_workspace_bytes", "ecf_wanda_layer_thresh_apply_batched", "ecf_group_reduce_chunk_elems",
     "ecf_group_abs_reduce", "ecf_zo_perturb", "ecf_count_zero", "ecf_hessian_accum", "ecf_obs_prune",
 )
@@ -47,7 +47,14 @@ class LayerDesc(C.Structure):
                 ("mask_ld", C.c_int64), ("n_zero", C.c_void_p)]
 
 
+class RowDesc(C.Structure):
+    _fields_ = [("W", C.c_void_p), ("scaler_row", C.c_void_p), ("R", C.c_int64), ("C", C.c_int64), ("ld", C.c_int64),
+                ("dtype", C.c_int32), ("k_per_row", C.c_int64), ("mask_bits", C.c_void_p), ("mask_ld", C.c_int64),
+                ("n_zero", C.c_void_p)]
+
+
 LAYER_MAX_BATCH = 8
+ROW_MAX_BATCH = 16
 SQNORM_MAX_BATCH = 256
 SQNORM_MAX_GROUPS = 32
 
@@ -69,6 +76,7 @@ def _load():
         "ecf_sqnorm_batched_workspace_bytes": (sz, [C.POINTER(SqnormDesc), i32]),
         "ecf_sqnorm_accum_batched": (i32, [C.POINTER(SqnormDesc), i32, vp, sz, vp]),
         "ecf_wanda_row_select_apply": (i32, [vp, i32, i64, i64, i64, vp, i64, vp, i64, vp, vp, sz, vp]),
+        "ecf_wanda_row_select_apply_batched": (i32, [C.POINTER(RowDesc), i32, vp, sz, vp]),
         "ecf_wanda_layer_thresh_apply": (i32, [vp, i32, i64, i64, i64, vp, i64, vp, vp, i64, vp, vp, sz, vp]),
         "ecf_layer_thresh_batched_workspace_bytes": (sz, [C.POINTER(LayerDesc), i32]),
         "ecf_wanda_layer_thresh_apply_batched": (i32, [C.POINTER(LayerDesc), i32, vp, sz, vp]),

@@ -21,7 +21,7 @@
 // Bound: HBM.  Algorithmic bytes per call: 2*R*C*sizeof(w) + 4*C.
 #include <cstdlib>
 
-#include "common.cuh"
+#include "row_select_fast.cuh"
 
 namespace ecf {
 
@@ -307,9 +307,9 @@ static int run_row_select(void* W, int64_t R, int64_t C, int64_t ld, const float
   return dispatch_nv<DT, false>(nv, W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
 }
 
-int row_select_fast_f16(void*, int64_t, int64_t, int64_t, const float*, int64_t, int, bool, uint8_t*, int64_t, unsigned long long*, cudaStream_t);
-int row_select_fast_bf16(void*, int64_t, int64_t, int64_t, const float*, int64_t, int, bool, uint8_t*, int64_t, unsigned long long*, cudaStream_t);
-int row_select_fast_f32(void*, int64_t, int64_t, int64_t, const float*, int64_t, int, bool, uint8_t*, int64_t, unsigned long long*, cudaStream_t);
+int row_select_fast_f16(RfBatch&, int, bool, cudaStream_t);
+int row_select_fast_bf16(RfBatch&, int, bool, cudaStream_t);
+int row_select_fast_f32(RfBatch&, int, bool, cudaStream_t);
 
 // tuning / A-B switches (read once): ECF_RS_NVMAX = vectors per lane cap of the fast kernel (1..8),
 // ECF_RS_KEEP=0 makes 16-bit rows with > 4 vectors per lane re-read the weights in the apply pass (fewer registers),
@@ -321,40 +321,88 @@ static int rs_env(const char* name, int dflt) {
 
 }  // namespace ecf
 
-extern "C" int ecf_wanda_row_select_apply(void* W, int w_dtype, int64_t R, int64_t C, int64_t ld,
-                                          const float* scaler_row, int64_t k_per_row, uint8_t* mask_bits,
-                                          int64_t mask_ld, unsigned long long* n_zero, void* ws, size_t ws_bytes,
-                                          ecf_stream_t stream) {
+namespace ecf {
+
+static int rs_check(const ecf_row_desc& d, int i) {
+  ECF_REQUIRE(d.W != nullptr && d.scaler_row != nullptr, ECF_ERR_INVALID, "row_select: null pointer (matrix %d)", i);
+  ECF_REQUIRE(d.R >= 0 && d.C > 0 && d.ld >= d.C, ECF_ERR_INVALID, "row_select: bad shape R=%lld C=%lld ld=%lld (matrix %d)",
+              (long long)d.R, (long long)d.C, (long long)d.ld, i);
+  ECF_REQUIRE(d.k_per_row >= 0, ECF_ERR_INVALID, "row_select: negative k (matrix %d)", i);
+  ECF_REQUIRE(d.mask_bits == nullptr || d.mask_ld >= (d.C + 7) / 8, ECF_ERR_INVALID, "row_select: mask_ld too small (matrix %d)", i);
+  ECF_REQUIRE(d.dtype >= 0 && d.dtype <= 2, ECF_ERR_INVALID, "row_select: unknown dtype %d (matrix %d)", d.dtype, i);
+  return ECF_OK;
+}
+
+static bool rs_fast_ok(const ecf_row_desc& d) {
+  const int vec = d.dtype == ECF_F32 ? 4 : 8;
+  return (d.C % 8 == 0) && (d.ld % vec == 0) && ((reinterpret_cast<uintptr_t>(d.W) & 15) == 0) && d.C <= 32768;
+}
+
+}  // namespace ecf
+
+extern "C" int ecf_wanda_row_select_apply_batched(const ecf_row_desc* descs, int n, void* ws, size_t ws_bytes, ecf_stream_t stream) {
   using namespace ecf;
   (void)ws;
   (void)ws_bytes;
   int st = check_device();
   if (st != ECF_OK) return st;
-  ECF_REQUIRE(W != nullptr && scaler_row != nullptr, ECF_ERR_INVALID, "row_select: null pointer");
-  ECF_REQUIRE(R >= 0 && C > 0 && ld >= C, ECF_ERR_INVALID, "row_select: bad shape R=%lld C=%lld ld=%lld",
-              (long long)R, (long long)C, (long long)ld);
-  ECF_REQUIRE(k_per_row >= 0, ECF_ERR_INVALID, "row_select: negative k");
-  ECF_REQUIRE(mask_bits == nullptr || mask_ld >= (C + 7) / 8, ECF_ERR_INVALID, "row_select: mask_ld too small");
-  if (R == 0) return ECF_OK;
-  if (k_per_row > C) k_per_row = C;  // sort_res[1][:, :k] clamps like python slicing
+  ECF_REQUIRE(descs != nullptr && n >= 1 && n <= ECF_ROW_MAX_BATCH, ECF_ERR_INVALID, "row_select: batch size %d outside [1, %d]", n,
+              ECF_ROW_MAX_BATCH);
+  for (int i = 0; i < n; ++i) {
+    if ((st = rs_check(descs[i], i)) != ECF_OK) return st;
+    for (int j = 0; j < i; ++j)
+      ECF_REQUIRE(descs[j].W != descs[i].W, ECF_ERR_INVALID, "row_select: matrices %d and %d are the same tensor", j, i);
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   static const int nv_max = [] { int v = rs_env("ECF_RS_NVMAX", 8); return v < 1 ? 1 : (v > 8 ? 8 : v); }();
   static const bool force_generic = rs_env("ECF_RS_GENERIC", 0) != 0;
   static const bool keep = rs_env("ECF_RS_KEEP", 0) != 0;
-  const int vec = w_dtype == ECF_F32 ? 4 : 8;
-  const bool aligned = (C % 8 == 0) && (ld % vec == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
-  if (aligned && !force_generic && C <= 32768 && w_dtype >= 0 && w_dtype <= 2) {
-    switch (w_dtype) {
-      case ECF_F32: return row_select_fast_f32(W, R, C, ld, scaler_row, k_per_row, nv_max, keep, mask_bits, mask_ld, n_zero, s);
-      case ECF_F16: return row_select_fast_f16(W, R, C, ld, scaler_row, k_per_row, nv_max, keep, mask_bits, mask_ld, n_zero, s);
-      case ECF_BF16: return row_select_fast_bf16(W, R, C, ld, scaler_row, k_per_row, nv_max, keep, mask_bits, mask_ld, n_zero, s);
+  bool done[ECF_ROW_MAX_BATCH];
+  for (int i = 0; i < n; ++i) done[i] = descs[i].R == 0;
+  for (int i = 0; i < n; ++i) {
+    if (done[i]) continue;
+    const ecf_row_desc& d0 = descs[i];
+    if (force_generic || !rs_fast_ok(d0)) {
+      // shape-generic kernel, one launch per matrix
+      const int64_t k = d0.k_per_row > d0.C ? d0.C : d0.k_per_row;  // sort_res[1][:, :k] clamps like python slicing
+      switch (d0.dtype) {
+        case ECF_F32: st = run_row_select<ECF_F32>(d0.W, d0.R, d0.C, d0.ld, d0.scaler_row, k, d0.mask_bits, d0.mask_ld, d0.n_zero, s); break;
+        case ECF_F16: st = run_row_select<ECF_F16>(d0.W, d0.R, d0.C, d0.ld, d0.scaler_row, k, d0.mask_bits, d0.mask_ld, d0.n_zero, s); break;
+        default: st = run_row_select<ECF_BF16>(d0.W, d0.R, d0.C, d0.ld, d0.scaler_row, k, d0.mask_bits, d0.mask_ld, d0.n_zero, s); break;
+      }
+      if (st != ECF_OK) return st;
+      done[i] = true;
+      continue;
     }
+    // every remaining matrix with this row length and dtype joins the launch
+    RfBatch tb;
+    tb.n = 0;
+    tb.C = (int)d0.C;
+    for (int j = i; j < n; ++j) {
+      const ecf_row_desc& d = descs[j];
+      if (done[j] || d.C != d0.C || d.dtype != d0.dtype || !rs_fast_ok(d)) continue;
+      RfMat& M = tb.m[tb.n++];
+      M.W = d.W; M.s = d.scaler_row; M.mask = d.mask_bits; M.n_zero = d.n_zero; M.R = d.R; M.ld = d.ld; M.mask_ld = d.mask_ld;
+      M.k = (int)(d.k_per_row > d.C ? d.C : d.k_per_row);
+      M.batch_begin = 0;
+      done[j] = true;
+    }
+    switch (d0.dtype) {
+      case ECF_F32: st = row_select_fast_f32(tb, nv_max, keep, s); break;
+      case ECF_F16: st = row_select_fast_f16(tb, nv_max, keep, s); break;
+      default: st = row_select_fast_bf16(tb, nv_max, keep, s); break;
+    }
+    if (st != ECF_OK) return st;
   }
-  switch (w_dtype) {
-    case ECF_F32: return run_row_select<ECF_F32>(W, R, C, ld, scaler_row, k_per_row, mask_bits, mask_ld, n_zero, s);
-    case ECF_F16: return run_row_select<ECF_F16>(W, R, C, ld, scaler_row, k_per_row, mask_bits, mask_ld, n_zero, s);
-    case ECF_BF16: return run_row_select<ECF_BF16>(W, R, C, ld, scaler_row, k_per_row, mask_bits, mask_ld, n_zero, s);
-  }
-  set_error("row_select: unknown dtype %d", w_dtype);
-  return ECF_ERR_INVALID;
+  return ECF_OK;
+}
+
+extern "C" int ecf_wanda_row_select_apply(void* W, int w_dtype, int64_t R, int64_t C, int64_t ld,
+                                          const float* scaler_row, int64_t k_per_row, uint8_t* mask_bits,
+                                          int64_t mask_ld, unsigned long long* n_zero, void* ws, size_t ws_bytes,
+                                          ecf_stream_t stream) {
+  ecf_row_desc d;
+  d.W = W; d.scaler_row = scaler_row; d.R = R; d.C = C; d.ld = ld; d.dtype = w_dtype; d.k_per_row = k_per_row;
+  d.mask_bits = mask_bits; d.mask_ld = mask_ld; d.n_zero = n_zero;
+  return ecf_wanda_row_select_apply_batched(&d, 1, ws, ws_bytes, stream);
 }

@@ -33,6 +33,23 @@ constexpr int kRfCap = 256;       // exact-ranking capacity per row
 constexpr int kRfBand = 32;       // stop narrowing once the bracket holds this many elements
 constexpr uint32_t kRfInf = 0x7c00u;  // fp16 +inf pattern: sorts after every real coarse key
 
+constexpr int kRfMaxMat = ECF_ROW_MAX_BATCH;  // matrices (same C, dtype) served by one launch
+
+// one matrix of a batched launch
+struct RfMat {
+  void* W;
+  const float* s;
+  uint8_t* mask;
+  unsigned long long* n_zero;
+  int64_t R, ld, mask_ld;
+  int k;
+  int batch_begin;  // first row batch (BLOCK / G rows) of this matrix in the launch
+};
+struct RfBatch {
+  RfMat m[kRfMaxMat];
+  int n, C, G, total_batches;
+};
+
 struct RfShared {
   int slots[2][kRfMaxGroups][kRfMaxWarps];
   uint32_t seed[kRfMaxGroups][2];
@@ -150,9 +167,7 @@ __device__ __forceinline__ void rf_mask_or(uint8_t* mask_row, uint32_t col) {
 
 template <int DT, int NV, bool MULTI, int BLOCK, bool KEEP>
 __global__ void __launch_bounds__(BLOCK, (BLOCK == 256 ? ((NV <= 4 || !KEEP) ? 3 : 2) : 1))
-    row_select_fast_kernel(void* __restrict__ W, int64_t R, int C, int64_t ld, const float* __restrict__ scaler_row, int k,
-                           int G, uint8_t* __restrict__ mask_bits, int64_t mask_ld,
-                           unsigned long long* __restrict__ n_zero) {
+    row_select_fast_kernel(const __grid_constant__ RfBatch tb) {
   constexpr int NP = 4 * NV;  // packed pairs per lane
   constexpr bool F32 = (DT == ECF_F32);
   constexpr bool REREAD = F32 || !KEEP;  // weights are not kept in registers: the apply pass re-reads the row (L2 hit)
@@ -160,10 +175,8 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 256 ? ((NV <= 4 || !KEEP) ? 3
   __shared__ RfShared sh;
 
   const int tid = threadIdx.x;
+  const int C = tb.C, G = tb.G;
   const int cpad = NV * G * 8;
-  for (int c = tid; c < cpad; c += BLOCK) qtab[c] = c < C ? __fadd_rn(sqrtf(scaler_row[c]), 0.f) : 0.f;
-  __syncthreads();
-
   const int group = tid / G;
   const int gl = tid - group * G;
   const int lane = tid & 31;
@@ -172,7 +185,34 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 256 ? ((NV <= 4 || !KEEP) ? 3
   int parity = 0;
   int zeros = 0;
 
-  for (int64_t row = (int64_t)blockIdx.x * rows_per_cta + group; row < R; row += (int64_t)gridDim.x * rows_per_cta) {
+  // a CTA owns a contiguous range of row batches: it crosses at most a couple of matrix boundaries, and at each
+  // one the whole CTA rebuilds sqrt(scaler_row) in shared memory
+  const int per = (tb.total_batches + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int bt0 = (int)blockIdx.x * per, bt1 = min(tb.total_batches, bt0 + per);
+  int mi = -1;
+  void* W = nullptr;
+  int64_t R = 0, ld = 0, mask_ld = 0;
+  uint8_t* mask_bits = nullptr;
+  unsigned long long* n_zero = nullptr;
+  int k = 0;
+
+  for (int bt = bt0; bt < bt1; ++bt) {
+    if (mi < 0 || bt >= tb.m[mi].batch_begin + (int)((tb.m[mi].R + rows_per_cta - 1) / rows_per_cta)) {
+      if (n_zero != nullptr) {
+        const int z = warp_sum(zeros);
+        if (lane == 0 && z) atomicAdd(n_zero, (unsigned long long)z);
+      }
+      zeros = 0;
+      if (mi < 0) mi = 0;
+      while (mi + 1 < tb.n && bt >= tb.m[mi + 1].batch_begin) ++mi;
+      const RfMat& M = tb.m[mi];
+      W = M.W; R = M.R; ld = M.ld; mask_bits = M.mask; mask_ld = M.mask_ld; n_zero = M.n_zero; k = M.k;
+      __syncthreads();  // every group is done with the previous matrix' table
+      for (int c = tid; c < cpad; c += BLOCK) qtab[c] = c < C ? __fadd_rn(sqrtf(M.s[c]), 0.f) : 0.f;
+      __syncthreads();
+    }
+    const int64_t row = (int64_t)(bt - tb.m[mi].batch_begin) * rows_per_cta + group;
+    if (row >= R) continue;
     char* wrow = reinterpret_cast<char*>(W) + row * ld * DType<DT>::kBytes;
     uint8_t* mask_row = mask_bits != nullptr ? mask_bits + row * mask_ld : nullptr;
     uint32_t co[NP];
@@ -410,9 +450,9 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 256 ? ((NV <= 4 || !KEEP) ? 3
 
 // ---------------------------------------------------------------------------------------------- host
 template <int DT, int NV, bool MULTI, int BLOCK, bool KEEP>
-static int rf_launch(void* W, int64_t R, int C, int64_t ld, const float* s, int k, int G, uint8_t* mask, int64_t mask_ld,
-                     unsigned long long* nz, cudaStream_t stream) {
+static int rf_launch(RfBatch& tb, cudaStream_t stream) {
   auto kern = row_select_fast_kernel<DT, NV, MULTI, BLOCK, KEEP>;
+  const int G = tb.G;
   const size_t smem = (size_t)NV * G * 8 * sizeof(float);
   static size_t smem_opted = 0;  // largest dynamic size this instantiation has been opted in for
   if (smem + sizeof(RfShared) > 48 * 1024 && smem > smem_opted) {
@@ -423,47 +463,54 @@ static int rf_launch(void* W, int64_t R, int C, int64_t ld, const float* s, int 
   ECF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem));
   if (occ < 1) occ = 1;
   const int rows_per_cta = BLOCK / G;
-  const int64_t batches = (R + rows_per_cta - 1) / rows_per_cta;
+  int64_t batches = 0;
+  for (int i = 0; i < tb.n; ++i) {
+    tb.m[i].batch_begin = (int)batches;
+    batches += (tb.m[i].R + rows_per_cta - 1) / rows_per_cta;
+  }
+  ECF_REQUIRE(batches < (1ll << 31), ECF_ERR_INVALID, "row_select: too many rows in one launch");
+  tb.total_batches = (int)batches;
   const int64_t cap = (int64_t)sm_count() * occ;
   const unsigned grid = (unsigned)(batches < cap ? batches : cap);
-  kern<<<grid, BLOCK, smem, stream>>>(W, R, C, ld, s, k, G, mask, mask_ld, nz);
+  kern<<<grid, BLOCK, smem, stream>>>(tb);
   ECF_CUDA_OK(cudaGetLastError());
   return ECF_OK;
 }
 
 template <int DT, int NV>
-static int rf_dispatch_g(void* W, int64_t R, int C, int64_t ld, const float* s, int k, int G, bool keep, uint8_t* mask,
-                         int64_t mask_ld, unsigned long long* nz, cudaStream_t stream) {
+static int rf_dispatch_g(RfBatch& tb, bool keep, cudaStream_t stream) {
+  const int G = tb.G;
   // KEEP only changes code for 16-bit weights with more than 4 vectors per lane (fp32 always re-reads)
   if constexpr (DT != ECF_F32 && NV > 4) {
     if (keep) {
-      if (G == 32) return rf_launch<DT, NV, false, 256, true>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
-      if (G <= 256) return rf_launch<DT, NV, true, 256, true>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
-      return rf_launch<DT, NV, true, 512, true>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
+      if (G == 32) return rf_launch<DT, NV, false, 256, true>(tb, stream);
+      if (G <= 256) return rf_launch<DT, NV, true, 256, true>(tb, stream);
+      return rf_launch<DT, NV, true, 512, true>(tb, stream);
     }
-    if (G == 32) return rf_launch<DT, NV, false, 256, false>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
-    if (G <= 256) return rf_launch<DT, NV, true, 256, false>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
-    return rf_launch<DT, NV, true, 512, false>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
+    if (G == 32) return rf_launch<DT, NV, false, 256, false>(tb, stream);
+    if (G <= 256) return rf_launch<DT, NV, true, 256, false>(tb, stream);
+    return rf_launch<DT, NV, true, 512, false>(tb, stream);
   } else {
-    if (G == 32) return rf_launch<DT, NV, false, 256, true>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
-    if (G <= 256) return rf_launch<DT, NV, true, 256, true>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
-    return rf_launch<DT, NV, true, 512, true>(W, R, C, ld, s, k, G, mask, mask_ld, nz, stream);
+    if (G == 32) return rf_launch<DT, NV, false, 256, true>(tb, stream);
+    if (G <= 256) return rf_launch<DT, NV, true, 256, true>(tb, stream);
+    return rf_launch<DT, NV, true, 512, true>(tb, stream);
   }
 }
 
-// Requires: C % 8 == 0, 16-byte aligned rows, C <= 32768.
+// Requires (every matrix of the batch): the same C with C % 8 == 0, 16-byte aligned rows, C <= 32768.
 template <int DT>
-static int run_row_select_fast(void* W, int64_t R, int64_t C, int64_t ld, const float* s, int64_t k, int nv_max, bool keep, uint8_t* mask,
-                               int64_t mask_ld, unsigned long long* nz, cudaStream_t stream) {
+static int run_row_select_fast(RfBatch& tb, int nv_max, bool keep, cudaStream_t stream) {
+  const int64_t C = tb.C;
   const int64_t nvec = C / 8;
   int G = 32;
   while (G < 512 && (nvec + G - 1) / G > nv_max) G <<= 1;
   int nv = (int)((nvec + G - 1) / G);
   ECF_REQUIRE(nv <= 8, ECF_ERR_INVALID, "row_select: C=%lld exceeds the supported row length 32768", (long long)C);
   if (nv == 7) nv = 8;
+  tb.G = G;
   switch (nv) {
 #define ECF_CASE(N) \
-  case N: return rf_dispatch_g<DT, N>(W, R, (int)C, ld, s, (int)k, G, keep, mask, mask_ld, nz, stream);
+  case N: return rf_dispatch_g<DT, N>(tb, keep, stream);
     ECF_CASE(1) ECF_CASE(2) ECF_CASE(3) ECF_CASE(4) ECF_CASE(5) ECF_CASE(6) ECF_CASE(8)
 #undef ECF_CASE
   }

@@ -135,6 +135,26 @@ def wanda_row_select_apply(W, scaler_row, k_per_row: int, mask_bits=None, n_zero
         n_zero.data_ptr() if n_zero is not None else None, None, 0, _stream(W)))
 
 
+def wanda_row_select_apply_batched(items) -> None:
+    """Per-row select of several matrices (the Linears of one block): matrices with the same row length and dtype
+    share one persistent launch.  ``items`` is a list of ``(W, scaler_row, k_per_row)`` or
+    ``(W, scaler_row, k_per_row, mask_bits, n_zero)`` tuples; lists longer than the ABI's batch limit are issued as
+    several calls."""
+    items = [tuple(it) + (None,) * (5 - len(it)) for it in items]
+    for start in range(0, len(items), _abi.ROW_MAX_BATCH):
+        chunk = items[start:start + _abi.ROW_MAX_BATCH]
+        descs = (_abi.RowDesc * len(chunk))()
+        for d, (W, scaler_row, k, mask_bits, n_zero) in zip(descs, chunk):
+            _require_cuda(W, scaler_row, mask_bits, n_zero)
+            R, C, ld = _weight_2d(W)
+            assert scaler_row.dtype == torch.float32 and scaler_row.numel() == C and scaler_row.is_contiguous()
+            d.W, d.scaler_row, d.R, d.C, d.ld, d.dtype, d.k_per_row = W.data_ptr(), scaler_row.data_ptr(), R, C, ld, dtype_code(W), int(k)
+            d.mask_bits = mask_bits.data_ptr() if mask_bits is not None else None
+            d.mask_ld = mask_bits.stride(0) if mask_bits is not None else 0
+            d.n_zero = n_zero.data_ptr() if n_zero is not None else None
+        check(lib.ecf_wanda_row_select_apply_batched(descs, len(chunk), None, 0, _stream(chunk[0][0])))
+
+
 def wanda_layer_thresh_apply(W, scaler_row, kth_index: int, thres_out=None, mask_bits=None, n_zero=None) -> None:
     """Zero, in place, every entry whose score is <= the kth_index-th smallest score (A3+A5+A7)."""
     _require_cuda(W, scaler_row, mask_bits, n_zero, thres_out)

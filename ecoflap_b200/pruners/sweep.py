@@ -195,7 +195,7 @@ def sweep_blocks(pruner, model, dataloader, device, spec: SweepSpec, model_prefi
             for h in handles:
                 h.remove()
 
-        layer_items = []
+        layer_items, row_items = [], []
         for name in subset:
             assert wrapped[name].nsamples == spec.expected_nsamples(inps), (
                 f"{name}: accumulated {wrapped[name].nsamples} samples, expected {spec.expected_nsamples(inps)}")
@@ -207,6 +207,11 @@ def sweep_blocks(pruner, model, dataloader, device, spec: SweepSpec, model_prefi
                 # every Linear of the block keeps its own exact threshold; they are selected in one cooperative launch
                 W = subset[name].weight.data
                 layer_items.append((W, wrapped[name].scaler_row, int(W.numel() * sparsity_ratio[key])))
+            elif method == "wanda" and spec.select == "row":
+                # k per row with the reference's Python expression (wanda_pruner.py:276); the Linears of the block that
+                # share a row length are selected in one launch
+                W = subset[name].weight.data
+                row_items.append((W, wrapped[name].scaler_row, int(W.shape[1] * sparsity_ratio[key])))
             elif method == "wanda":
                 wanda_prune_linear(subset[name], wrapped[name], sparsity_ratio[key], spec.select)
             else:
@@ -215,6 +220,8 @@ def sweep_blocks(pruner, model, dataloader, device, spec: SweepSpec, model_prefi
                 wrapped[name].free()
         if layer_items:
             ops.wanda_layer_thresh_apply_batched(layer_items)
+        if row_items:
+            ops.wanda_row_select_apply_batched(row_items)
         if restore is not None:
             restore()
 

@@ -113,6 +113,25 @@ ECF_API int ecf_wanda_row_select_apply(void* W, int w_dtype, int64_t R, int64_t 
                                uint8_t* mask_bits, int64_t mask_ld, unsigned long long* n_zero,
                                void* ws, size_t ws_bytes, ecf_stream_t stream);
 
+/* A3+A4+A7, batched -- the per-row select of all the Linears of a block (T5: q, k, v, o, wi_0, wi_1, wo; the
+ * reference prunes them one after the other, wanda_pruner.py:255-279) in as few launches as their shapes allow:
+ * matrices with the same row length C and dtype share ONE persistent launch (a 2048 x 2048 matrix alone is a single
+ * 15 us wave on 148 SMs).  Every matrix is pruned exactly as by ecf_wanda_row_select_apply.  `descs` is a HOST array
+ * of n <= ECF_ROW_MAX_BATCH distinct matrices. */
+#define ECF_ROW_MAX_BATCH 16
+typedef struct ecf_row_desc {
+  void* W;                    /* [R, C] weights, row-major, leading dimension ld (elements); pruned in place */
+  const float* scaler_row;    /* [C] fp32 */
+  int64_t R, C, ld;
+  int32_t dtype;              /* enum ecf_dtype of W */
+  int64_t k_per_row;          /* int(C * s), host-computed */
+  uint8_t* mask_bits;         /* nullable: packed mask, row stride mask_ld bytes */
+  int64_t mask_ld;
+  unsigned long long* n_zero; /* nullable: += zero-valued weights after the call */
+} ecf_row_desc;
+ECF_API int ecf_wanda_row_select_apply_batched(const ecf_row_desc* descs, int n,
+                                       void* ws, size_t ws_bytes, ecf_stream_t stream);
+
 /* A3+A5+A7 -- per-LAYER threshold select, wanda_pruner.py:541,553-558 (ViT); UPop :502,512-517;
  * prune_utils.py:28-31.  thres = kth_index-th (0-based) smallest score of the whole matrix; every
  * entry with score <= thres is zeroed in place (>= kth_index+1 entries, more on ties).

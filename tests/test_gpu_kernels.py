@@ -319,6 +319,35 @@ def test_row_select_strided_weight():
     assert torch.equal(big[:, :1024], before[:, :1024]) and torch.equal(big[:, 3072:], before[:, 3072:])
 
 
+def test_row_select_batched_equals_single_calls():
+    """The Linears of a T5 block in one call (same-C matrices share a launch; a ragged and an unaligned-view matrix take
+    the generic kernel; different k, masks and zero counts per matrix) against one call per matrix."""
+    from ecoflap_b200 import ops
+
+    shapes = [(2048, 2048), (517, 2048), (2048, 2048), (640, 5120), (1, 2048), (300, 2048), (33, 50), (64, 1408)]
+    ks = [1024, 1064, 0, 2560, 2048, 613, 25, 704]
+    Ws = [synth_w(r, c, "bf16", seed=17 * i + c).to(dev()) for i, (r, c) in enumerate(shapes)]
+    ss = [torch.from_numpy(synth_norm(c, seed=i + c)).to(dev()) for i, (r, c) in enumerate(shapes)]
+    single = [w.clone() for w in Ws]
+    m1 = [ops.alloc_mask_bits(r, c, dev()) for r, c in shapes]
+    z1 = [torch.zeros(1, dtype=torch.int64, device=dev()) for _ in shapes]
+    for w, s, k, m, z in zip(single, ss, ks, m1, z1):
+        ops.wanda_row_select_apply(w, s, k, mask_bits=m, n_zero=z)
+    batched = [w.clone() for w in Ws]
+    m2 = [ops.alloc_mask_bits(r, c, dev()) for r, c in shapes]
+    z2 = [torch.zeros(1, dtype=torch.int64, device=dev()) for _ in shapes]
+    ops.wanda_row_select_apply_batched([(w, s, k, m, z) for w, s, k, m, z in zip(batched, ss, ks, m2, z2)])
+    for i, (a, b) in enumerate(zip(single, batched)):
+        assert torch.equal(a, b), shapes[i]
+        assert torch.equal(m1[i], m2[i]), shapes[i]
+        assert int(z1[i].item()) == int(z2[i].item()), shapes[i]
+    # and against the oracle for one of them
+    ref, _ = orc.wanda_prune_rows(f32(Ws[1]), ss[1].cpu().numpy(), 1064 / 2048 + 1e-9)
+    assert np.array_equal(f32(batched[1]), ref)
+    with pytest.raises(Exception):  # the same tensor twice
+        ops.wanda_row_select_apply_batched([(batched[0], ss[0], 1), (batched[0], ss[0], 1)])
+
+
 # ---------------------------------------------------------------------------- A3+A5+A7
 LAYER_SHAPES = [(2304, 768), (768, 3072), (4224, 1408), (100, 50), (7, 96), (3, 8)]
 
