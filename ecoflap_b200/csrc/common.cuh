@@ -70,6 +70,16 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
                : "l"(p));
   return r;
 }
+// 16-byte coherent load that bypasses L1 allocation: streaming data the same kernel later overwrites in place, read next
+// to small tables (q = sqrt(scaler_row)) that must stay L1 resident
+__device__ __forceinline__ uint4 ldg_noalloc(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
 // 16-byte load that may be re-read by the same kernel / a follow-up pass (keep in L2)
 __device__ __forceinline__ uint4 ldg_v4(const void* p) {
   return *reinterpret_cast<const uint4*>(p);

@@ -46,7 +46,7 @@ struct LtMat {
   unsigned* coarse;         // workspace: [kLtCoarseBins] sample histogram (self-cleaning)
   unsigned* hist;           // workspace: [3][kLtBins] digit histograms (self-cleaning)
   unsigned long long* cnt;  // workspace: [0] #(key < lo), [1] #(lo <= key < hi)
-  uint32_t* bracket;        // workspace: [0] lo, [1] hi (coarse, hi exclusive, <= kLtTop), [3] P1 ticket
+  uint32_t* bracket;        // workspace: [0] lo, [1] hi (coarse, hi exclusive, <= kLtTop), [3] P1 ticket, [4] ~min / [5] max+1 occupied sample bin
   float* thres_out;
   uint8_t* mask;
   unsigned long long* n_zero;
@@ -332,56 +332,83 @@ __device__ __forceinline__ void lt_grid_barrier(unsigned* bar, unsigned& gen) {
   __syncthreads();
 }
 
-// One warp per matrix: find the bin of its 2 048-bin digit histogram (level `level`) that holds rank sel.rem.
-__device__ __forceinline__ void lt_find_bins(const LtBatch& b, LtSel* sel, int level) {
+// Four warps per matrix: find the bin of its 2 048-bin digit histogram (level `level`) that holds rank sel.rem.
+// Every lane reads its 16 bins with four coalesced 128-bit loads that are all in flight together and keeps them in
+// registers for the search (one L2 round trip instead of a chain of them).
+__device__ __forceinline__ void lt_find_bins(const LtBatch& b, LtSel* sel, int level, unsigned long long (*sh_q)[4]) {
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (wid < b.n && sel[wid].nd > level) {
-    constexpr int PER = kLtBins / 32;  // 64 consecutive bins per lane
-    const uint4* my = reinterpret_cast<const uint4*>(b.m[wid].hist + level * kLtBins + lane * PER);
-    unsigned long long sum = 0;
-#pragma unroll 4
-    for (int j = 0; j < PER / 4; ++j) {
-      const uint4 v = __ldcg(my + j);
-      sum += (unsigned long long)v.x + v.y + v.z + v.w;
-    }
-    unsigned long long inc = sum;
+  constexpr int kPerRound = kLtThreads / 32 / 4;  // matrices handled per round
+  for (int m0 = 0; m0 < b.n; m0 += kPerRound) {
+    const int mi = m0 + (wid >> 2), qt = wid & 3;
+    const bool on = mi < b.n && sel[mi < b.n ? mi : 0].nd > level;
+    uint4 v[4];
+    unsigned long long inc[4], tot[4], quarter = 0;
+    if (on) {
+      const uint4* src = reinterpret_cast<const uint4*>(b.m[mi].hist + level * kLtBins + qt * (kLtBins / 4));
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    const unsigned long long rem = sel[wid].rem;
-    unsigned long long run = inc - sum;
-    __syncwarp();
-    if (rem >= run && rem < run + sum) {  // exactly one lane
-      for (int j = 0; j < PER / 4; ++j) {
-        const uint4 v = __ldcg(my + j);
-        const unsigned cs[4] = {v.x, v.y, v.z, v.w};
+      for (int j = 0; j < 4; ++j) v[j] = __ldcg(src + j * 32 + lane);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (rem >= run && rem < run + cs[e]) {
-            sel[wid].prefix = (sel[wid].prefix << 11) | (uint32_t)(lane * PER + 4 * j + e);
-            sel[wid].rem = rem - run;
-            sel[wid].done = level + 1;
+      for (int j = 0; j < 4; ++j) {
+        unsigned long long x = (unsigned long long)v[j].x + v[j].y + v[j].z + v[j].w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned long long t = __shfl_up_sync(0xffffffffu, x, o);
+          if (lane >= o) x += t;
+        }
+        inc[j] = x;
+        tot[j] = __shfl_sync(0xffffffffu, x, 31);
+        quarter += tot[j];
+      }
+      if (lane == 0) sh_q[wid >> 2][qt] = quarter;
+    }
+    __syncthreads();
+    if (on) {
+      unsigned long long run = 0;
+      for (int q = 0; q < qt; ++q) run += sh_q[wid >> 2][q];
+      const unsigned long long rem = sel[mi].rem;
+      if (rem >= run && rem < run + quarter) {  // exactly one warp
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (rem >= run && rem < run + tot[j]) {  // exactly one chunk (warp-uniform)
+            const unsigned cs[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+            const unsigned long long mine = (unsigned long long)cs[0] + cs[1] + cs[2] + cs[3];
+            unsigned long long r2 = run + inc[j] - mine;  // elements before this lane's first bin
+            if (rem >= r2 && rem < r2 + mine) {  // exactly one lane
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (rem >= r2 && rem < r2 + cs[e]) {
+                  sel[mi].prefix = (sel[mi].prefix << 11) | (uint32_t)(qt * (kLtBins / 4) + (j * 32 + lane) * 4 + e);
+                  sel[mi].rem = rem - r2;
+                  sel[mi].done = level + 1;
+                }
+                r2 += cs[e];
+              }
+            }
           }
-          run += cs[e];
+          run += tot[j];
         }
       }
     }
+    __syncthreads();
   }
-  __syncthreads();
 }
 
-// P2: the calling CTA turns the sample histogram of matrix M into a coarse bracket (and cleans the histogram)
+// P2: the calling CTA turns the sample histogram of matrix M into a coarse bracket (and cleans the histogram).
+// Only the occupied bin range [bmin, bmax) recorded by the sampling CTAs is scanned: typically a few hundred bins,
+// i.e. one or two per thread, instead of 64.
 __device__ __forceinline__ void lt_bracket(const LtMat& M, unsigned long long* sh_scan /*[36]*/) {
   const int tid = threadIdx.x;
-  constexpr int PER = kLtCoarseBins / kLtThreads;  // 64 consecutive bins per thread, read as 16 independent 128-bit loads
-  const uint4* my_bins = reinterpret_cast<const uint4*>(M.coarse + tid * PER);
+  const uint32_t enc_min = __ldcg(M.bracket + 4), bmax = min(__ldcg(M.bracket + 5), (uint32_t)kLtTop);
+  const uint32_t bmin = min(0xffffffffu - enc_min, bmax);
+  const uint32_t per = (bmax - bmin + kLtThreads - 1) / kLtThreads;
+  const uint32_t b0 = min(bmax, bmin + (uint32_t)tid * per), b1 = min(bmax, b0 + per);
   unsigned long long sum = 0;
-#pragma unroll 8
-  for (int j = 0; j < PER / 4; ++j) {
-    const uint4 v = __ldcg(my_bins + j);
-    sum += (unsigned long long)v.x + v.y + v.z + v.w;
+  for (uint32_t bin = b0; bin < b1; bin += 8) {
+    unsigned c[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) c[u] = bin + u < b1 ? __ldcg(M.coarse + bin + u) : 0u;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) sum += c[u];
   }
   const int lane = tid & 31, wid = tid >> 5;
   unsigned long long inc = sum;
@@ -410,6 +437,8 @@ __device__ __forceinline__ void lt_bracket(const LtMat& M, unsigned long long* s
       reinterpret_cast<long long*>(sh_scan)[33] = rs + delta;
       M.bracket[0] = 0u;
       M.bracket[1] = kLtTop;
+      M.bracket[4] = 0u;  // occupied range: empty again for the next launch
+      M.bracket[5] = 0u;
       M.cnt[0] = 0ull;
       M.cnt[1] = 0ull;
     }
@@ -418,24 +447,20 @@ __device__ __forceinline__ void lt_bracket(const LtMat& M, unsigned long long* s
   const long long r_lo = reinterpret_cast<long long*>(sh_scan)[32], r_hi = reinterpret_cast<long long*>(sh_scan)[33];
   unsigned long long run = sh_scan[wid] + inc - sum;  // samples in the bins before this thread's first bin
   if (sum) {  // only threads whose bins hold samples can contain the two ranks
-#pragma unroll 4
-    for (int j = 0; j < PER / 4; ++j) {
-      const uint4 v = __ldcg(my_bins + j);
-      const unsigned cs[4] = {v.x, v.y, v.z, v.w};
+    for (uint32_t bin = b0; bin < b1; bin += 8) {
+      unsigned c[8];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const unsigned long long c = cs[e];
-        const int bin = tid * PER + 4 * j + e;
-        if (c) {
-          if (r_lo >= 0 && (unsigned long long)r_lo >= run && (unsigned long long)r_lo < run + c) M.bracket[0] = (uint32_t)bin;
-          if (r_hi >= 0 && (unsigned long long)r_hi >= run && (unsigned long long)r_hi < run + c) M.bracket[1] = (uint32_t)bin + 1u;
+      for (int u = 0; u < 8; ++u) c[u] = bin + u < b1 ? __ldcg(M.coarse + bin + u) : 0u;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (c[u]) {
+          if (r_lo >= 0 && (unsigned long long)r_lo >= run && (unsigned long long)r_lo < run + c[u]) M.bracket[0] = bin + u;
+          if (r_hi >= 0 && (unsigned long long)r_hi >= run && (unsigned long long)r_hi < run + c[u]) M.bracket[1] = bin + u + 1u;
+          M.coarse[bin + u] = 0u;  // self-cleaning for the next launch
         }
-        run += c;
+        run += c[u];
       }
     }
-#pragma unroll
-    for (int j = 0; j < PER / 4; ++j)  // self-cleaning for the next launch
-      reinterpret_cast<uint4*>(M.coarse + tid * PER)[j] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
 }
@@ -448,8 +473,10 @@ __global__ void __launch_bounds__(kLtThreads, 2) layer_thresh_batched_kernel(con
   uint32_t* sh_list = sh_dyn + b.n * kLtBins;
   __shared__ unsigned sh_cnt[kLtMaxMat][2];  // per-CTA counts fit 32 bits (a CTA sees < 2^32 elements)
   __shared__ unsigned long long sh_scan[36];
+  __shared__ unsigned long long sh_q[kLtThreads / 32 / 4][4];
   __shared__ LtSel sel[kLtMaxMat];
   __shared__ unsigned sh_list_n;
+  __shared__ unsigned sh_range[2];
   __shared__ int sh_overflow, sh_last;
   const int tid = threadIdx.x, lane = tid & 31;
   const int64_t gthreads = (int64_t)gridDim.x * kLtThreads;
@@ -474,6 +501,7 @@ __global__ void __launch_bounds__(kLtThreads, 2) layer_thresh_batched_kernel(con
     // CTA c samples slice c / n of matrix c % n into a shared-memory histogram (16-bit counters, two per word) and
     // adds its non-empty bins to the global one: ~300 global REDs per CTA instead of one per sample on a few hundred
     // hot addresses.  The last CTA of a matrix (ticket) goes straight on to P2 for it: no grid barrier in between.
+    if (tid == 0) sh_range[0] = sh_range[1] = 0u;
     const int nslices = max(1, (int)gridDim.x / b.n);
     const int mi = (int)blockIdx.x % b.n, slice = (int)blockIdx.x / b.n;
     if (slice < nslices) {
@@ -505,10 +533,29 @@ __global__ void __launch_bounds__(kLtThreads, 2) layer_thresh_batched_kernel(con
           }
         }
         __syncthreads();
+        unsigned wmin = 0xffffffffu, wmax = 0u;  // occupied words of this CTA's histogram
         for (int i = tid; i < kLtSampWords; i += kLtThreads) {
           const unsigned w = sh_dyn[i];
+          if (w) {
+            wmin = min(wmin, (unsigned)i);
+            wmax = max(wmax, (unsigned)i + 1u);
+          }
           if (w & 0xffffu) atomicAdd(M.coarse + 2 * i, w & 0xffffu);
           if (w >> 16) atomicAdd(M.coarse + 2 * i + 1, w >> 16);
+        }
+        wmin = __reduce_min_sync(0xffffffffu, wmin);
+        wmax = __reduce_max_sync(0xffffffffu, wmax);
+        if (lane == 0 && wmax) {  // both encoded so that a zeroed workspace means "empty": max of (~min) and of (max)
+          atomicMax(&sh_range[0], 0xffffffffu - 2u * wmin);
+          atomicMax(&sh_range[1], 2u * wmax);
+        }
+        __syncthreads();
+        if (tid == 0) {
+          if (sh_range[1]) {
+            atomicMax(M.bracket + 4, sh_range[0]);
+            atomicMax(M.bracket + 5, sh_range[1]);
+          }
+          sh_range[0] = sh_range[1] = 0u;
         }
         __syncthreads();
       }
@@ -692,7 +739,7 @@ __global__ void __launch_bounds__(kLtThreads, 2) layer_thresh_batched_kernel(con
   int max_nd = 1;
   for (int mi = 0; mi < b.n; ++mi) max_nd = max(max_nd, sel[mi].nd);
   for (int level = 0; level < max_nd; ++level) {
-    lt_find_bins(b, sel, level);  // every CTA computes the same bins
+    lt_find_bins(b, sel, level, sh_q);  // every CTA computes the same bins
     lt_stamp(b, 9 + 3 * (level > 0 ? 1 : 0));
     if (level + 1 >= max_nd) break;
     // histogram of the next digit for the elements matching the prefix
