@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out; O=gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; tail -5 $O/pytest_gpu.log
+
 timeout 900 python bench.py --no-cpu > $O/bench.json 2> $O/bench.err; tail -3 $O/bench.err; python - <<'PY'
 import json
 d=json.loads(open("gpurun_out/bench.json").read().strip().splitlines()[-1])
