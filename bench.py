@@ -256,6 +256,8 @@ def run_b200(args):
 
     side = [torch.cuda.Stream(device=dev) for _ in range(max(len(pb) for pb in lins))]
 
+    ROW_SHARD = os.environ.get("ECF_ROW_SHARD", "0") == "1"  # row-sharded select + all-gather instead of replication
+
     def step_device():
         """one pass, everything resident in HBM.  Per block: the hook calls of its 16 calibration batches are
         deferred into batched norm launches (<= 256 hook calls / 32 accumulators each), then the fused select of
@@ -265,19 +267,23 @@ def run_b200(args):
         for pb in lins:
             nb = NormBatch()
             accs = [WrappedGPT(o.layer, batch=nb) for o in pb]
+            flat = edist.pack_block_norms(accs) if world > 1 else None  # one buffer per block: one in-place all-reduce
             for j in range(N_BATCHES):
                 for o, acc in zip(pb, accs):
                     acc.add_batch(o.acts[j])
             nb.flush()
             layer_items = [(o.W, acc.scaler_row, o.idx) for o, acc in zip(pb, accs) if o.spec.select == "layer"]
             if world > 1:
-                edist.sync_block_norms(accs)
-                for o, acc in zip(pb, accs):
-                    if o.spec.select == "row":
-                        edist.row_sharded_select(o.W, lambda sh, a=acc, k=o.k: ops.wanda_row_select_apply(sh, a.scaler_row, k))
-                if layer_items:
-                    ops.wanda_layer_thresh_apply_batched(layer_items)
-                continue
+                # equal shards: the global mean is the average of the rank means -- one NCCL all-reduce (AVG) per block on
+                # the packed norm buffer, nothing read back, so the whole step stays capturable in one CUDA graph
+                edist.sync_packed_norms(flat, accs)
+                if ROW_SHARD:
+                    for o, acc in zip(pb, accs):
+                        if o.spec.select == "row":
+                            edist.row_sharded_select(o.W, lambda sh, a=acc, k=o.k: ops.wanda_row_select_apply(sh, a.scaler_row, k))
+                    if layer_items:
+                        ops.wanda_layer_thresh_apply_batched(layer_items)
+                    continue
             if layer_items:  # the per-layer selects of a block: one cooperative launch
                 ops.wanda_layer_thresh_apply_batched(layer_items)
             rows = [(o.W, acc.scaler_row, o.k) for o, acc in zip(pb, accs) if o.spec.select == "row"]
@@ -535,14 +541,21 @@ def run_b200(args):
                                       f"(distinct norm input bytes per step {summ['unique_norm_input_bytes']})",
                        "l2": "inputs larger than L2: 47 GB touched per step, no buffer re-read within 126 MB",
                        "timing": "CUDA events per step, max over ranks; weights restored between steps outside the events",
-                       "bracket_ms": bracket_ms, "launch": launch_mode, "parallelism": f"dp{world}: batch-sharded norms + NCCL all-reduce, row-sharded select"},
+                       "bracket_ms": bracket_ms, "launch": launch_mode, "parallelism": f"dp{world}: batch-sharded norms + NCCL all-reduce per block; select " + ("row-sharded + all-gather" if ROW_SHARD and world > 1 else "replicated per rank")},
             "prune_wall_s_hot_path": step_ms * 1e-3,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks, "abi_version": _abi.lib.ecf_version(),
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # The captured step holds NCCL work; tearing the communicator down under live CUDA graphs can block for
+        # minutes.  Everything is measured and printed: synchronise, meet the other ranks, and leave without running
+        # the destructors.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

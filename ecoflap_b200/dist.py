@@ -5,8 +5,10 @@ One process per GPU, ``torch.distributed`` (NCCL over NVLink/NVSwitch on the box
   * calibration batches are sharded round-robin over the ranks; every rank accumulates the running mean of
     sum x^2 (or the Hessian) over ITS samples; one all-reduce per block over the concatenated per-Linear
     vectors turns them into the global mean  sum_r n_r * s_r / sum_r n_r  (latency bound: <= 35 k floats);
-  * per-ROW mask selection is sharded over output rows (rows are independent): rank r selects rows
-    [r*R/P, (r+1)*R/P) in place and an all-gather rebuilds the pruned matrix on every rank;
+  * per-ROW mask selection can be sharded over output rows (rows are independent): rank r selects rows
+    [r*R/P, (r+1)*R/P) in place and an all-gather rebuilds the pruned matrix on every rank.  Measured on B200 the
+    all-gather (NVLink, ~0.9 TB/s per direction) costs more than it saves against the replicated HBM-bound select
+    (> 2 TB/s of algorithmic bytes), so replication is the default and sharding an option (bench: ECF_ROW_SHARD=1);
   * the per-LAYER threshold select and the OBS sweep are replicated (their exchange steps are future work).
 
 The collective plumbing below works on CPU and CUDA tensors alike; the kernels are only reached through the
@@ -41,33 +43,72 @@ def row_range(rows: int, rank: int, world: int):
     return rank * per, (rank + 1) * per
 
 
-def allreduce_running_means(stats: Sequence[torch.Tensor], counts: Sequence[int], group=None):
+def allreduce_running_means(stats: Sequence[torch.Tensor], counts: Sequence[int], group=None, totals: Sequence[int] = None):
     """In place: every tensor in ``stats`` (a per-rank running mean over ``counts[i]`` samples) becomes the
-    mean over the samples of all ranks.  One all-reduce for the whole list.  Returns the global counts."""
+    mean over the samples of all ranks.  One all-reduce for the whole list.  Returns the global counts.
+
+    ``totals``: the global sample counts when the caller already knows them (equal shards: count * world).  The
+    counts then stay on the host, nothing is read back from the device and the call can be captured in a CUDA graph;
+    without it the counts ride along in the all-reduce and are read back (one host sync)."""
     if not stats:
         return []
     flat = torch.cat([(s.reshape(-1) * float(n)) for s, n in zip(stats, counts)])
+    if totals is not None:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        off = 0
+        for s, tot in zip(stats, totals):
+            n = s.numel()
+            s.copy_((flat[off:off + n] * (1.0 / float(tot))).reshape(s.shape))
+            off += n
+        return [int(t) for t in totals]
     tail = torch.tensor([float(n) for n in counts], dtype=flat.dtype, device=flat.device)
     buf = torch.cat([flat, tail])
     dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-    totals = buf[flat.numel():]
+    totals_dev = buf[flat.numel():]
     off = 0
     out_counts = []
     for i, s in enumerate(stats):
         n = s.numel()
-        tot = totals[i]
+        tot = totals_dev[i]
         s.copy_((buf[off:off + n] / tot).reshape(s.shape))
         off += n
         out_counts.append(int(round(float(tot))))
     return out_counts
 
 
-def sync_block_norms(accumulators, group=None):
+def sync_block_norms(accumulators, group=None, totals: Sequence[int] = None):
     """accumulators: WrappedGPT-like objects (.scaler_row fp32 [C], .nsamples)."""
     accs = list(accumulators)
-    totals = allreduce_running_means([a.scaler_row for a in accs], [a.nsamples for a in accs], group)
+    totals = allreduce_running_means([a.scaler_row for a in accs], [a.nsamples for a in accs], group, totals)
     for a, n in zip(accs, totals):
         a.nsamples = n
+
+
+def pack_block_norms(accumulators) -> torch.Tensor:
+    """Rebind the (still empty) norm accumulators of a block to slices of ONE flat fp32 buffer, so that the block's
+    exchange step is a single in-place all-reduce with no gather / scatter kernels around it.  Returns the buffer."""
+    accs = list(accumulators)
+    flat = torch.zeros(sum(a.columns for a in accs), dtype=torch.float32, device=accs[0].dev)
+    off = 0
+    for a in accs:
+        assert a.nsamples == 0, "pack_block_norms must run before the first add_batch"
+        a.scaler_row = flat[off:off + a.columns]
+        off += a.columns
+    return flat
+
+
+def sync_packed_norms(flat: torch.Tensor, accumulators, group=None):
+    """Exchange step for accumulators packed by ``pack_block_norms`` when every rank holds the same number of samples:
+    the global running mean is the average of the per-rank means -- one all-reduce (NCCL: ReduceOp.AVG), in place."""
+    _, world = rank_world(group)
+    if world > 1:
+        if dist.get_backend(group) == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            flat.mul_(1.0 / world)
+    for a in accumulators:
+        a.nsamples *= world
 
 
 def sync_block_hessians(accumulators, group=None):

@@ -52,6 +52,36 @@ def _worker(rank, world, port, out_dir):
     np.testing.assert_allclose(accs[0].scaler_row.numpy(), full.scaler_row, rtol=1e-5)
     np.testing.assert_allclose(accs[1].scaler_row.numpy(), 4.0 * full.scaler_row, rtol=1e-5)
 
+    # packed variant: the block's accumulators are slices of one buffer, exchanged by ONE in-place all-reduce; with
+    # known totals nothing is read back (capturable in a CUDA graph on the box)
+    class PAcc:
+        def __init__(self, scale):
+            self.columns, self.dev, self.nsamples, self.scale = C, torch.device("cpu"), 0, scale
+            self.scaler_row = torch.zeros(C)
+            self.ref = orc.NormAccumulator(C)
+
+        def add(self, x):  # in place: scaler_row is a view of the packed buffer
+            self.scaler_row.copy_(torch.from_numpy(self.ref.add_batch(self.scale * x).copy()))
+            self.nsamples = self.ref.nsamples
+
+    paccs = [PAcc(1.0), PAcc(2.0)]
+    flat = edist.pack_block_norms(paccs)
+    assert flat.numel() == 2 * C and paccs[1].scaler_row.data_ptr() == flat.data_ptr() + 4 * C
+    for j in mine:
+        for a in paccs:
+            a.add(batches[j])
+    edist.sync_packed_norms(flat, paccs)
+    assert paccs[0].nsamples == n_batches * B
+    np.testing.assert_allclose(paccs[0].scaler_row.numpy(), full.scaler_row, rtol=1e-5)
+    np.testing.assert_allclose(flat[C:].numpy(), 4.0 * full.scaler_row, rtol=1e-5)
+    taccs = [Acc(), Acc()]
+    for j in mine:
+        taccs[0].add(batches[j])
+        taccs[1].add(2.0 * batches[j])
+    edist.sync_block_norms(taccs, totals=[n_batches * B] * 2)
+    np.testing.assert_allclose(taccs[1].scaler_row.numpy(), 4.0 * full.scaler_row, rtol=1e-5)
+    assert taccs[0].nsamples == n_batches * B
+
     # Hessians go through the same plumbing
     class HAcc:
         def __init__(self):
