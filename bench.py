@@ -418,9 +418,20 @@ def run_b200(args):
     for v in kernels.values():
         v["time_share"] = v["time_share"] / tot_ms
     dominant = max(kernels, key=lambda k: kernels[k]["time_share"])
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (per launch; the capture's launch
+    # is named next to it -- traffic ~= algorithmic bytes means no wasted re-reads)
+    traffic, traffic_of = None, None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1", "traffic.json")) as fh:
+            tr = json.load(fh).get(dominant)
+        if tr:
+            traffic = tr["dram_bytes_per_launch"]
+            traffic_of = {"launch": tr["launch"], "algorithmic_bytes_per_launch": tr["algorithmic_bytes_per_launch"], "source": tr["source"]}
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": kernels[dominant]["achieved_gbs"], "peak": peak,
-                "unit": "GB/s", "frac": kernels[dominant]["frac"], "traffic": None, "peak_source": peak_src,
-                "kernels": kernels}
+                "unit": "GB/s", "frac": kernels[dominant]["frac"], "traffic": traffic, "traffic_of": traffic_of,
+                "peak_source": peak_src, "kernels": kernels}
 
     # ---- e2e: host buffers through the public API ------------------------------------------------------------
     e2e = None

@@ -19,7 +19,10 @@ CASES = {
     "big": [(131072, 4096, f16, 1)],
 }
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+NCU_CASE = sys.argv[2] if len(sys.argv) > 2 and sys.argv[1] == "ncu" else None
 for name, spec in CASES.items():
+    if NCU_CASE is not None and name != NCU_CASE:
+        continue
     nb = 1 if name in ("single_T5", "big") else (8 if name == "llama_qkv" else NB)
     items, alg, distinct = [], 0, 0
     for (T, C, dt, nlin) in spec:
@@ -31,8 +34,12 @@ for name, spec in CASES.items():
                 items.append((x, s, j / (j + 1.0), 1.0 / (8 * (j + 1))))
                 alg += T * C * x.element_size() + 8 * C
     for _ in range(3):
+        flush.zero_()
         ops.sqnorm_accum_batched(items)
     torch.cuda.synchronize()
+    if NCU_CASE is not None:
+        print(name, "algorithmic bytes", alg, "distinct bytes", distinct)
+        continue
     # the launch is replayed from a CUDA graph so that the host-side descriptor marshalling is not in the timing
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
