@@ -257,6 +257,15 @@ def run_b200(args):
     side = [torch.cuda.Stream(device=dev) for _ in range(max(len(pb) for pb in lins))]
 
     ROW_SHARD = os.environ.get("ECF_ROW_SHARD", "0") == "1"  # row-sharded select + all-gather instead of replication
+    # exchange step of the norms: our peer-memory kernel over NVSwitch (22 us per block at 8 GPUs) unless it is
+    # unavailable or switched off (ECF_P2P_EXCHANGE=0), then one NCCL all-reduce per block (36 us at 8 GPUs)
+    pex = None
+    if world > 1 and os.environ.get("ECF_P2P_EXCHANGE", "1") != "0" and edist.PeerNormExchange.available():
+        try:
+            pex = edist.PeerNormExchange(max(sum(o.spec.cols for o in pb) for pb in lins), dev)
+        except Exception as exc:  # pragma: no cover - rendezvous unsupported on this box: say so, use NCCL
+            print(f"[bench] peer-memory exchange unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
+            pex = None
 
     def step_device():
         """one pass, everything resident in HBM.  Per block: the hook calls of its 16 calibration batches are
@@ -276,7 +285,10 @@ def run_b200(args):
             if world > 1:
                 # equal shards: the global mean is the average of the rank means -- one NCCL all-reduce (AVG) per block on
                 # the packed norm buffer, nothing read back, so the whole step stays capturable in one CUDA graph
-                edist.sync_packed_norms(flat, accs)
+                if pex is not None:
+                    pex.sync(flat, accs)
+                else:
+                    edist.sync_packed_norms(flat, accs)
                 if ROW_SHARD:
                     for o, acc in zip(pb, accs):
                         if o.spec.select == "row":
@@ -552,7 +564,7 @@ def run_b200(args):
                                       f"(distinct norm input bytes per step {summ['unique_norm_input_bytes']})",
                        "l2": "inputs larger than L2: 47 GB touched per step, no buffer re-read within 126 MB",
                        "timing": "CUDA events per step, max over ranks; weights restored between steps outside the events",
-                       "bracket_ms": bracket_ms, "launch": launch_mode, "parallelism": f"dp{world}: batch-sharded norms + NCCL all-reduce per block; select " + ("row-sharded + all-gather" if ROW_SHARD and world > 1 else "replicated per rank")},
+                       "bracket_ms": bracket_ms, "launch": launch_mode, "parallelism": f"dp{world}: batch-sharded norms + " + ("peer-memory exchange kernel (NVSwitch P2P)" if pex is not None else "NCCL all-reduce") + " per block; select " + ("row-sharded + all-gather" if ROW_SHARD and world > 1 else "replicated per rank")},
             "prune_wall_s_hot_path": step_ms * 1e-3,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks, "abi_version": _abi.lib.ecf_version(),

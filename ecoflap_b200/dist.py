@@ -111,6 +111,55 @@ def sync_packed_norms(flat: torch.Tensor, accumulators, group=None):
         a.nsamples *= world
 
 
+class PeerNormExchange:
+    """Exchange step of the norm accumulators over NVSwitch peer memory (``ecf_norm_exchange_p2p``): one small fused
+    copy / signal / gather-sum kernel per rank and block instead of an NCCL all-reduce.  torch's symmetric-memory
+    rendezvous supplies the peer mappings of the staging buffer (plumbing); the exchange itself is our kernel.
+
+    ``available()`` is False off-GPU, for non-NCCL groups, or when the rendezvous is not supported; callers then use
+    ``sync_packed_norms`` (NCCL)."""
+
+    def __init__(self, max_floats: int, device, group=None):
+        import ctypes
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _abi
+
+        self._abi = _abi
+        self.rank, self.world = rank_world(group)
+        self.max_floats = (int(max_floats) + 3) // 4 * 4
+        nbytes = _abi.lib.ecf_norm_exchange_staging_bytes(self.max_floats)
+        self.staging = symm_mem.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
+        self.staging.zero_()
+        torch.cuda.synchronize(device)
+        grp = group if group is not None else dist.group.WORLD
+        self.handle = symm_mem.rendezvous(self.staging, grp)
+        dist.barrier(group)  # every rank's flags are zero before anybody signals
+        ptrs = list(self.handle.buffer_ptrs)
+        assert len(ptrs) == self.world and self.handle.rank == self.rank
+        self._ptrs = (ctypes.c_void_p * self.world)(*ptrs)
+
+    @staticmethod
+    def available(group=None) -> bool:
+        try:
+            if not (torch.cuda.is_available() and is_dist() and str(dist.get_backend(group)) == "nccl"):
+                return False
+            import torch.distributed._symmetric_memory as _sm  # noqa: F401
+            return hasattr(_sm, "rendezvous") and hasattr(_sm, "empty")
+        except Exception:
+            return False
+
+    def sync(self, flat: torch.Tensor, accumulators=()):
+        """flat (fp32, contiguous, CUDA) <- mean over ranks, in place; accumulators' sample counts are scaled."""
+        assert flat.dtype == torch.float32 and flat.is_contiguous() and flat.numel() <= self.max_floats
+        abi = self._abi
+        abi.check(abi.lib.ecf_norm_exchange_p2p(flat.data_ptr(), flat.numel(), self._ptrs, self.max_floats, self.rank, self.world,
+                                                torch.cuda.current_stream(flat.device).cuda_stream))
+        for a in accumulators:
+            a.nsamples *= self.world
+
+
 def sync_block_hessians(accumulators, group=None):
     accs = list(accumulators)
     totals = allreduce_running_means([a.H for a in accs], [a.nsamples for a in accs], group)

@@ -162,6 +162,18 @@ ECF_API size_t ecf_layer_thresh_batched_workspace_bytes(const ecf_layer_desc* de
 ECF_API int ecf_wanda_layer_thresh_apply_batched(const ecf_layer_desc* descs, int n,
                                          void* ws, size_t ws_bytes, ecf_stream_t stream);
 
+/* A1 / A8 exchange step on one NVSwitch box (the reference is single-GPU): average a packed fp32
+ * vector (the norm accumulators of a block) over the ranks through PEER MEMORY, in place -- a fused copy / signal /
+ * gather-sum kernel per rank instead of an NCCL all-reduce.  `peer_staging` is a HOST array of `world` device pointers:
+ * rank r's staging buffer as mapped into this process (ecf_norm_exchange_staging_bytes(max_floats) bytes each, zeroed
+ * once, symmetric across ranks; the host obtains the mappings from torch's symmetric-memory rendezvous).  Every rank
+ * must make the same sequence of calls (same n).  All ranks end with bit-identical results (rank-ordered sums). */
+#define ECF_EXCHANGE_MAX_WORLD 16
+#define ECF_EXCHANGE_MAX_CTAS 32
+ECF_API size_t ecf_norm_exchange_staging_bytes(int64_t max_floats);
+ECF_API int ecf_norm_exchange_p2p(float* local, int64_t n, void* const* peer_staging, int64_t max_floats,
+                                  int rank, int world, ecf_stream_t stream);
+
 /* A14 -- group aggregation, layer_single_base_pruner.py:361-377 together with the |W| / W^2 factors
  * of :467,:556-559.  One launch over a DEVICE table of tensors; per tensor i:
  *   sum_abs[i] = sum |w|,  sum_sq[i] = sum w^2      (fp32 partials, fp64 final combine)
