@@ -356,7 +356,8 @@ extern "C" int ecf_wanda_row_select_apply_batched(const ecf_row_desc* descs, int
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   static const int nv_max = [] { int v = rs_env("ECF_RS_NVMAX", 8); return v < 1 ? 1 : (v > 8 ? 8 : v); }();
   static const bool force_generic = rs_env("ECF_RS_GENERIC", 0) != 0;
-  static const bool keep = rs_env("ECF_RS_KEEP", 0) != 0;
+  static const bool keep = rs_env("ECF_RS_KEEP", 1) != 0;
+  static const int prefetch = rs_env("ECF_RS_PREFETCH", 0);
   bool done[ECF_ROW_MAX_BATCH];
   for (int i = 0; i < n; ++i) done[i] = descs[i].R == 0;
   for (int i = 0; i < n; ++i) {
@@ -378,6 +379,7 @@ extern "C" int ecf_wanda_row_select_apply_batched(const ecf_row_desc* descs, int
     RfBatch tb;
     tb.n = 0;
     tb.C = (int)d0.C;
+    tb.prefetch = prefetch;
     for (int j = i; j < n; ++j) {
       const ecf_row_desc& d = descs[j];
       if (done[j] || d.C != d0.C || d.dtype != d0.dtype || !rs_fast_ok(d)) continue;

@@ -48,6 +48,7 @@ struct RfMat {
 struct RfBatch {
   RfMat m[kRfMaxMat];
   int n, C, G, total_batches;
+  int prefetch;  // issue L2 prefetches for a group's next row (A/B switch ECF_RS_PREFETCH)
 };
 
 struct RfShared {
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 256 ? ((NV <= 4 || !KEEP) ? 3
   __shared__ RfShared sh;
 
   const int tid = threadIdx.x;
+  const bool PREFETCH = tb.prefetch != 0;
   const int C = tb.C, G = tb.G;
   const int cpad = NV * G * 8;
   const int group = tid / G;
@@ -213,6 +215,18 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 256 ? ((NV <= 4 || !KEEP) ? 3
     }
     const int64_t row = (int64_t)(bt - tb.m[mi].batch_begin) * rows_per_cta + group;
     if (row >= R) continue;
+    if (PREFETCH && bt + 1 < bt1 && row + rows_per_cta < R) {
+      // the group's next row starts its trip from HBM to L2 now; its loads (a whole selection later) then miss L1 only
+      const char* nrow = reinterpret_cast<const char*>(W) + (row + rows_per_cta) * ld * DType<DT>::kBytes;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c0 = (i * G + gl) * 8;
+        if (c0 < C) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + (int64_t)c0 * DType<DT>::kBytes));
+          if constexpr (F32) asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + (int64_t)c0 * 4 + 16));
+        }
+      }
+    }
     char* wrow = reinterpret_cast<char*>(W) + row * ld * DType<DT>::kBytes;
     uint8_t* mask_row = mask_bits != nullptr ? mask_bits + row * mask_ld : nullptr;
     uint32_t co[NP];

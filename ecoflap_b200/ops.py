@@ -135,6 +135,22 @@ def wanda_row_select_apply(W, scaler_row, k_per_row: int, mask_bits=None, n_zero
         n_zero.data_ptr() if n_zero is not None else None, None, 0, _stream(W)))
 
 
+def wanda_nm_select_apply(W, scaler_row, n: int, m: int, mask_bits=None, n_zero=None) -> None:
+    """n:m structured select (A6): zero, in place, the n smallest |W|*sqrt(scaler_row) of every group of m consecutive
+    columns.  Raises like ``torch.topk`` when a group is shorter than n."""
+    _require_cuda(W, scaler_row, mask_bits, n_zero)
+    R, C, ld = _weight_2d(W)
+    assert scaler_row.dtype == torch.float32 and scaler_row.numel() == C and scaler_row.is_contiguous()
+    last = C % m if C % m else m
+    if n > m or n > last:
+        raise RuntimeError("selected index k out of range")  # torch.topk's message
+    check(lib.ecf_wanda_nm_select_apply(
+        W.data_ptr(), dtype_code(W), R, C, ld, scaler_row.data_ptr(), int(n), int(m),
+        mask_bits.data_ptr() if mask_bits is not None else None,
+        mask_bits.stride(0) if mask_bits is not None else 0,
+        n_zero.data_ptr() if n_zero is not None else None, _stream(W)))
+
+
 def wanda_row_select_apply_batched(items) -> None:
     """Per-row select of several matrices (the Linears of one block): matrices with the same row length and dtype
     share one persistent launch.  ``items`` is a list of ``(W, scaler_row, k_per_row)`` or

@@ -89,14 +89,15 @@ class _Uniform:
 
 
 def _run(args, model, dataloader, device, prune_n, prune_m, method):
-    if prune_n != 0:
-        raise NotImplementedError("n:m sparsity (2:4 / 4:8) is not part of the ECoFLaP recipes")
+    if prune_n != 0 and method != "wanda":
+        raise NotImplementedError("n:m SparseGPT (2:4 / 4:8) is not part of the ECoFLaP recipes")
     use_cache = getattr(model.config, "use_cache", None)
     if use_cache is not None:
         model.config.use_cache = False
     try:
         ratios = _ratios(args, model, dataloader)
         pruner = _LlamaSweepPruner(model, dataloader, method=method, prune_spec=None)
+        pruner.prune_n, pruner.prune_m = int(prune_n), int(prune_m)  # --sparsity_type 2:4 / 4:8 (LLaMA/main.py:55-58)
         with torch.no_grad():
             pruner._prune(model, dataloader, device, "model.layers", getattr(args, "nsamples", 128), ratios)
     finally:

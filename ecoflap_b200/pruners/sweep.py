@@ -201,9 +201,12 @@ def sweep_blocks(pruner, model, dataloader, device, spec: SweepSpec, model_prefi
                 f"{name}: accumulated {wrapped[name].nsamples} samples, expected {spec.expected_nsamples(inps)}")
             print(f"pruning layer {i} name {name}")
             key = spec.sparsity_key(module_to_process, i, name)
-            if pruner.prune_n != 0:
-                raise NotImplementedError("n:m sparsity is dead code in the reference (prune_n = prune_m = 0)")
-            if method == "wanda" and spec.select == "layer":
+            if pruner.prune_n != 0 and method != "wanda":
+                raise NotImplementedError("n:m SparseGPT is dead code in the reference recipes (prune_n = prune_m = 0)")
+            if method == "wanda" and pruner.prune_n != 0:
+                # structured n:m branch (wanda_pruner.py:265-270 / :546-551): same for the row and the layer variants
+                ops.wanda_nm_select_apply(subset[name].weight.data, wrapped[name].scaler_row, pruner.prune_n, pruner.prune_m)
+            elif method == "wanda" and spec.select == "layer":
                 # every Linear of the block keeps its own exact threshold; they are selected in one cooperative launch
                 W = subset[name].weight.data
                 layer_items.append((W, wrapped[name].scaler_row, int(W.numel() * sparsity_ratio[key])))

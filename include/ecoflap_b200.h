@@ -132,6 +132,15 @@ typedef struct ecf_row_desc {
 ECF_API int ecf_wanda_row_select_apply_batched(const ecf_row_desc* descs, int n,
                                        void* ws, size_t ws_bytes, ecf_stream_t stream);
 
+/* A6 -- n:m structured Wanda select, wanda_pruner.py:265-270 (T5), :546-551 (ViT); the 2:4 / 4:8 modes of the LLaMA
+ * CLI (LLaMA/main.py:35,55-58).  In every group of m consecutive columns of a row the n smallest scores are zeroed in
+ * place (ties -> lower column; torch.topk leaves the tie order unspecified).  1 <= m <= 32.  A last group shorter
+ * than n (or n > m) returns ECF_ERR_RANGE: torch.topk raises there.  n == 0 is a no-op. */
+ECF_API int ecf_wanda_nm_select_apply(void* W, int w_dtype, int64_t R, int64_t C, int64_t ld,
+                              const float* scaler_row, int n, int m,
+                              uint8_t* mask_bits, int64_t mask_ld, unsigned long long* n_zero,
+                              ecf_stream_t stream);
+
 /* A3+A5+A7 -- per-LAYER threshold select, wanda_pruner.py:541,553-558 (ViT); UPop :502,512-517;
  * prune_utils.py:28-31.  thres = kth_index-th (0-based) smallest score of the whole matrix; every
  * entry with score <= thres is zeroed in place (>= kth_index+1 entries, more on ties).

@@ -348,6 +348,63 @@ def test_row_select_batched_equals_single_calls():
         ops.wanda_row_select_apply_batched([(batched[0], ss[0], 1), (batched[0], ss[0], 1)])
 
 
+# ---------------------------------------------------------------------------- A6
+@pytest.mark.parametrize("dt", ["fp16", "bf16", "fp32"])
+@pytest.mark.parametrize("nm", [(2, 4), (4, 8), (1, 4), (3, 8), (2, 3), (5, 16), (1, 1)])
+@pytest.mark.parametrize("shape", [(64, 2048), (33, 1408), (7, 96), (5, 50)])
+def test_nm_select_bit_exact(dt, nm, shape):
+    """n:m structured select (wanda_pruner.py:265-270): masks and pruned weights against the oracle; ragged last
+    groups; groups shorter than n raise like torch.topk."""
+    from ecoflap_b200 import ops
+
+    n, m = nm
+    R, C = shape
+    W = synth_w(R, C, dt, seed=R + 7 * C + n)
+    W[1, : min(C, 16)] = W[1, 0]          # ties inside groups: lower column first
+    W[2] = 0                              # all-zero row: the first n of every group
+    s = synth_norm(C, seed=C + m)
+    last = C % m if C % m else m
+    Wd = W.clone().to(dev())
+    mb = ops.alloc_mask_bits(R, C, dev())
+    nz = torch.zeros(1, dtype=torch.int64, device=dev())
+    if n > last:
+        with pytest.raises(Exception):
+            ops.wanda_nm_select_apply(Wd, torch.from_numpy(s).to(dev()), n, m, mask_bits=mb, n_zero=nz)
+        return
+    ops.wanda_nm_select_apply(Wd, torch.from_numpy(s).to(dev()), n, m, mask_bits=mb, n_zero=nz)
+    mref = orc.nm_select_mask(orc.wanda_metric(f32(W), s), n, m)
+    Wref = orc.apply_mask(f32(W), mref)
+    assert np.array_equal(f32(Wd).view(np.uint32), Wref.view(np.uint32)), (dt, nm, shape)
+    assert np.array_equal(ops.unpack_mask_bits(mb, C).cpu().numpy(), mref)
+    assert int(nz.item()) == orc.count_zero(Wref)
+    assert int(mref.sum()) == R * ((C // m) * n + (n if C % m else 0))
+
+
+def test_nm_select_full_size_and_view():
+    """2:4 on a LLaMA-sized matrix: every group of 4 keeps its 2 largest scores; strided views stay inside their columns."""
+    from ecoflap_b200 import ops
+
+    R, C = 11008, 4096
+    W = synth_w(R, C, "fp16", seed=3).to(dev())
+    s = torch.from_numpy(synth_norm(C, seed=4)).to(dev())
+    score = W.float().abs() * s.sqrt()
+    ops.wanda_nm_select_apply(W, s, 2, 4)
+    z = (W == 0).view(R, C // 4, 4)
+    assert bool((z.sum(-1) >= 2).all())
+    sc = score.view(R, C // 4, 4)
+    pruned_max = torch.where(z, sc, torch.full_like(sc, -1.0)).max(-1).values
+    kept_min = torch.where(z, torch.full_like(sc, float("inf")), sc).min(-1).values
+    assert bool((pruned_max <= kept_min).all())
+    big = synth_w(16, 4096, "bf16", seed=9).to(dev())
+    view = big[:, 1024:3072]
+    before = big.clone()
+    sv = synth_norm(2048, seed=3)
+    ops.wanda_nm_select_apply(view, torch.from_numpy(sv).to(dev()), 4, 8)
+    ref = orc.apply_mask(f32(before[:, 1024:3072]), orc.nm_select_mask(orc.wanda_metric(f32(before[:, 1024:3072]), sv), 4, 8))
+    assert np.array_equal(f32(view), ref)
+    assert torch.equal(big[:, :1024], before[:, :1024]) and torch.equal(big[:, 3072:], before[:, 3072:])
+
+
 # ---------------------------------------------------------------------------- A3+A5+A7
 LAYER_SHAPES = [(2304, 768), (768, 3072), (4224, 1408), (100, 50), (7, 96), (3, 8)]
 

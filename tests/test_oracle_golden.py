@@ -143,3 +143,24 @@ def test_select_steps_match_reference_prune_loop(golden):
         got, mask = orc.wanda_prune_rows(W, s, 0.5)
         assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), i
         assert (mask.sum(axis=1) == int(W.shape[1] * 0.5)).all()
+
+
+def test_nm_select_oracle_matches_the_reference_expression():
+    """A6: the oracle's n:m mask against the reference's own expression (wanda_pruner.py:265-270:
+    ``W_mask.scatter_(1, ii + torch.topk(tmp, prune_n, dim=1, largest=False)[1], True)`` per group of prune_m columns)
+    evaluated with torch on tie-free scores, where torch.topk's unspecified tie order cannot matter."""
+    import torch
+
+    rng = np.random.default_rng(7)
+    for (R, C, n, m) in [(16, 64, 2, 4), (9, 96, 4, 8), (5, 50, 2, 3), (4, 40, 1, 4), (3, 32, 5, 16)]:
+        W = (rng.standard_normal((R, C)) * 0.02).astype(np.float32)
+        s = (rng.random(C) + 0.1).astype(np.float32)
+        M = orc.wanda_metric(W, s)
+        assert len(np.unique(M)) == M.size  # tie-free
+        W_metric = torch.abs(torch.from_numpy(W)) * torch.sqrt(torch.from_numpy(s).reshape((1, -1)))
+        W_mask = (torch.zeros_like(W_metric) == 1)
+        for ii in range(W_metric.shape[1]):
+            if ii % m == 0:
+                tmp = W_metric[:, ii:(ii + m)].float()
+                W_mask.scatter_(1, ii + torch.topk(tmp, n, dim=1, largest=False)[1], True)
+        assert np.array_equal(orc.nm_select_mask(M, n, m), W_mask.numpy()), (R, C, n, m)

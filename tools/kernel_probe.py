@@ -70,6 +70,19 @@ for (R, C, dt) in [] if not want('layer_thresh') else [(4224, 1408, torch.float1
     gb = (2 * R * C * W.element_size() + 4 * C) / 1e9
     out.append(dict(k="layer_thresh", R=R, C=C, dt=str(dt), ms=ms, GBs=gb / ms * 1e3, frac=gb / ms * 1e3 / PEAK))
     print(out[-1], flush=True)
+for (R, C, dt, n, m) in [] if not want('nm_select') else [(11008, 4096, torch.float16, 2, 4), (4096, 11008, torch.float16, 4, 8), (5120, 2048, torch.bfloat16, 2, 4)]:
+    W0 = (torch.randn(R, C, device=dev) * 0.02).to(dt)
+    s = torch.rand(C, device=dev) + 0.1
+    W = W0.clone()
+    ts = []
+    for _ in range(12):
+        W.copy_(W0); flush.zero_(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ops.wanda_nm_select_apply(W, s, n, m); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    ts.sort(); ms = ts[len(ts) // 2]
+    gb = (2 * R * C * W.element_size() + 4 * C) / 1e9
+    out.append(dict(k="nm_select", R=R, C=C, dt=str(dt), nm=f"{n}:{m}", ms=ms, GBs=gb / ms * 1e3, frac=gb / ms * 1e3 / PEAK))
+    print(out[-1], flush=True)
 if not want('misc'):
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open("gpurun_out/kernel_probe_%s.json" % os.environ.get("PROBE_TAG", "x"), "w"), indent=1)
