@@ -32,6 +32,27 @@ def rank_world(group=None):
     return 0, 1
 
 
+def zo_draws_per_layer(batch_lens: Sequence[int], num_samples: int, num_noise: int) -> int:
+    """How many (batch, noise) evaluations -- i.e. ``np.random.randint`` seed draws -- the reference's zeroth-order loop
+    makes for ONE parameter (layer_single_base_pruner.py:515-547): ``seen`` grows by the batch length per noise draw
+    and both loops stop once it reaches ``num_samples``.  ``batch_lens``: batch lengths in loader order."""
+    seen, draws = 0, 0
+    for bl in batch_lens:
+        if seen >= num_samples:
+            break
+        for _ in range(num_noise):
+            if seen >= num_samples:
+                break
+            seen += int(bl)
+            draws += 1
+    return draws
+
+
+def zo_owner(layer_index: int, world: int) -> int:
+    """Layer -> rank assignment of the sharded zeroth-order loop: l = r (mod P)."""
+    return layer_index % world
+
+
 def shard_indices(n: int, rank: int, world: int):
     """Round-robin ownership of calibration batches: j = rank (mod world)."""
     return list(range(rank, n, world))

@@ -178,6 +178,10 @@ class LayerSparsity:
 
     # ------------------------------------------------------------------ A12 zeroth-order scores
     def compute_importance_scores_mezo(self, layer_to_group_mapping):
+        from . import dist as edist
+
+        if edist.is_dist():
+            return self._compute_importance_scores_mezo_sharded(layer_to_group_mapping)
         model, loss_func = self.model, self.loss_func
         model.eval()
         names, params = self._selected(layer_to_group_mapping)
@@ -207,6 +211,74 @@ class LayerSparsity:
                     acc += abs(((loss_plus - loss_minus) / (2 * eps)).item())
                     torch.manual_seed(seed)
                 ghat[name] += acc
+        return self._mezo_scores(names, params, ghat)
+
+    def _compute_importance_scores_mezo_sharded(self, layer_to_group_mapping):
+        """The zeroth-order loop on P ranks (the reference is single-GPU): the (layer, batch) grid is
+        embarrassingly parallel over layers, so rank r evaluates the layers l = r (mod P) on a replicated model and one
+        all-reduce of the [#layers] g-hat vector ends the stage -- 2 * #layers * #batches forwards become
+        2 * #layers * #batches / P per GPU.  What is reproduced of the single-GPU run:
+          * the numpy seed stream, pre-drawn in the reference's (layer, batch, noise) order on every rank (the number of
+            draws per layer comes from one unperturbed pass over the first-stage batches), hence every z;
+          * the weights stage 2 scores: every owner broadcasts its perturbed-and-inexactly-restored parameters afterwards
+            (SURVEY A11: one +1/-2/+1 cycle changes ~45 % of the elements), bit-identical to the sequential loop;
+          * g-hat up to the rounding residue of the OTHER ranks' layers: the sequential loop evaluates layer i on a
+            model whose layers < i already carry that residue (<= 5e-3 relative in bf16, 7e-8 in fp32), here only the
+            rank's own earlier layers do -- both losses of a pair see the same residue, so the effect is second order."""
+        import torch.distributed as dist
+
+        from . import dist as edist
+
+        model, loss_func = self.model, self.loss_func
+        model.eval()
+        names, params = self._selected(layer_to_group_mapping)
+        device = next(iter(model.parameters())).device
+        eps = self.noise_eps
+        rank, world = edist.rank_world()
+        # one unperturbed pass: batch lengths -> seed draws per layer
+        batch_lens, seen = [], 0
+        for batch in self.data_loader:
+            if seen >= self.num_samples:
+                break
+            with torch.no_grad():
+                _, batch_len = loss_func(model, batch, device != "cpu")
+            batch_lens.append(int(batch_len))
+            seen += int(batch_len)
+        draws = edist.zo_draws_per_layer(batch_lens, self.num_samples, self.num_noise)
+        seeds = [[int(np.random.randint(1000000000)) for _ in range(draws)] for _ in names]  # the reference's stream
+        ghat_vec = torch.zeros(len(names), dtype=torch.float64, device=device)
+        for i, (name, param) in enumerate(zip(names, params)):
+            if edist.zo_owner(i, world) != rank:
+                continue
+            print(i, name)
+            seen, d, total = 0, 0, 0.0
+            for batch in self.data_loader:
+                if seen >= self.num_samples:
+                    break
+                acc = 0.0
+                for _ in range(self.num_noise):
+                    if seen >= self.num_samples:
+                        break
+                    seed = seeds[i][d]
+                    d += 1
+                    self.zo_perturb_parameters([param], random_seed=seed, scaling_factor=1, zo_eps=eps)
+                    with torch.no_grad():
+                        loss_plus, batch_len = loss_func(model, batch, device != "cpu")
+                    self.zo_perturb_parameters([param], random_seed=seed, scaling_factor=-2, zo_eps=eps)
+                    with torch.no_grad():
+                        loss_minus, batch_len = loss_func(model, batch, device != "cpu")
+                    self.zo_perturb_parameters([param], random_seed=seed, scaling_factor=1, zo_eps=eps)
+                    seen += batch_len
+                    acc += abs(((loss_plus - loss_minus) / (2 * eps)).item())
+                total += acc
+            assert d == draws, "the first-stage loader changed between passes"
+            ghat_vec[i] = total
+        dist.all_reduce(ghat_vec, op=dist.ReduceOp.SUM)
+        for i, param in enumerate(params):  # every rank continues with the weights the single-GPU loop would leave
+            dist.broadcast(param.data, src=edist.zo_owner(i, world))
+        if draws and names:
+            torch.manual_seed(seeds[-1][-1])
+        ghat = {k: float(ghat_vec[i].item()) for i, k in enumerate(names)}
         return self._mezo_scores(names, params, ghat)
 
     def _mezo_scores(self, names, params, ghat):
