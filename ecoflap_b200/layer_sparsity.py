@@ -298,14 +298,24 @@ class LayerSparsity:
     def compute_importance_scores(self, layer_to_group_mapping):
         """mean over batches of |dL/dW| (or g^2), then |W|*|g| / W^2*g / |g| (:416-471).  Gradients stay on the
         device (the reference copies 3.7 G fp32 elements to the host per batch); only sum(score) is kept."""
+        from . import dist as edist
+
         model, loss_func = self.model, self.loss_func
         names, params = self._selected(layer_to_group_mapping)
         device = next(iter(model.parameters())).device
         acc = {k: None for k in names}
         seen, nbatches = 0, 0
-        for batch in self.data_loader:
+        # P ranks (SURVEY 8e A13): data parallel over the first-stage batches, rank r takes batch j = r (mod P).  Every
+        # score is linear in the per-batch |g| (or g^2) terms, so the ranks exchange one scalar per layer at the end
+        # instead of gradients.
+        rank, world = edist.rank_world() if edist.is_dist() else (0, 1)
+        for j, batch in enumerate(self.data_loader):
             if seen >= self.num_samples:
                 break
+            if world > 1 and j % world != rank:
+                seen += self._batch_len(batch, device)
+                nbatches += 1
+                continue
             loss, batch_len = loss_func(model, batch, device != "cpu")
             seen += batch_len
             nbatches += 1
@@ -317,6 +327,8 @@ class LayerSparsity:
                 acc[k] = term if acc[k] is None else acc[k].add_(term)
         scores = {}
         for k, p in zip(names, params):
+            if acc[k] is None:  # this rank saw no batch (more ranks than batches)
+                acc[k] = torch.zeros_like(p, dtype=torch.float32)
             gbar = acc[k] / nbatches
             w = p.detach().float()
             if "GradMagSquare" in self.score_compute:
@@ -327,5 +339,24 @@ class LayerSparsity:
                 s = gbar.abs().sum()
             else:
                 raise ValueError(f"unknown first-order score method {self.score_compute!r}")
-            scores[k] = s.reshape(1).cpu()
-        return scores
+            scores[k] = s.reshape(1)
+        if world > 1:
+            import torch.distributed as dist
+
+            vec = torch.cat([scores[k].double() for k in names])
+            dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+            scores = {k: vec[i:i + 1].float() for i, k in enumerate(names)}
+        return {k: v.cpu() for k, v in scores.items()}
+
+    def _batch_len(self, batch, device):
+        """Length of a first-stage batch this rank does not evaluate (the stopping rule counts every batch): the
+        conventions of the reference's loss closures (utils.py:21-66, CoOp zsclip.py:61-95, UPop tuple batches), else
+        one forward."""
+        if isinstance(batch, dict):
+            for key in ("text_input", "image", "label", "labels", "img", "input_ids"):
+                if key in batch:
+                    return len(batch[key])
+        if isinstance(batch, (list, tuple)) and len(batch) and hasattr(batch[0], "shape"):
+            return int(batch[0].shape[0])
+        with torch.no_grad():
+            return int(self.loss_func(self.model, batch, device != "cpu")[1])

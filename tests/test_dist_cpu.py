@@ -201,6 +201,25 @@ def _zo_worker(rank, world, port, out_dir):
     for k in s_seq:
         np.testing.assert_allclose(s_sh[k].numpy(), s_seq[k].numpy(), rtol=1e-3)
     assert edist.zo_draws_per_layer([5, 5, 5, 5], 12, 2) == 3 and edist.zo_draws_per_layer([8] * 16, 32, 1) == 4
+
+    # first-order scores (A13): data parallel over the batches, one scalar per layer exchanged
+    def run_first_order(sharded, method):
+        model = make_model()
+        mapping = {k: k for k, v in model.named_parameters() if v.dim() == 2}
+        ls = CpuLayerSparsity(model, loader, loss_func, num_samples=15, original_sparsity=0.5, max_sparsity_per_layer=0.8,
+                              score_method=method, layer_to_group_mapping=mapping)
+        real = edist.is_dist
+        if not sharded:
+            edist.is_dist = lambda: False
+        try:
+            return ls.compute_importance_scores(mapping)
+        finally:
+            edist.is_dist = real
+
+    for method in ("GradMagAbs_sum", "GradMagSquare_avg", "GradOnly_sum"):
+        f_seq, f_sh = run_first_order(False, method), run_first_order(True, method)
+        for k in f_seq:
+            np.testing.assert_allclose(f_sh[k].numpy(), f_seq[k].numpy(), rtol=1e-5)
     dist.barrier()
     with open(os.path.join(out_dir, f"zo_ok_{rank}"), "w") as fh:
         fh.write("ok")
