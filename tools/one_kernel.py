@@ -17,7 +17,10 @@ if which == "layer_block":
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for _ in range(reps):
         Ws = [w.clone() for w in W0]
-        flush.zero_()
+        if os.environ.get("FLUSH", "write") == "read":
+            flush.sum()      # evicts with CLEAN lines (what a preceding streaming-read kernel leaves in L2)
+        else:
+            flush.zero_()    # evicts with DIRTY lines: the kernel's reads also pay their write-back
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         ops.wanda_layer_thresh_apply_batched([(w, s, w.numel() // 2) for w, s in zip(Ws, ss)])
