@@ -160,3 +160,16 @@ def test_fp16_bf16_models_run():
                                                                   model_prefix="t5_model")).prune()
     z = [(p == 0).float().mean().item() for n, p in t5.named_parameters() if p.dim() == 2 and ".block." in n and "relative" not in n]
     assert all(v == 0.5 for v in z)
+
+
+def test_kept_parameter_percentage_matches_torch():
+    """evaluate_blip.py:432-436 counted on the device (ecf_count_zero) against the reference's torch expression."""
+    from ecoflap_b200 import driver_io
+
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(64, 96), torch.nn.Linear(96, 32)).cuda().half()
+    with torch.no_grad():
+        model[0].weight[:, ::3] = 0
+        model[1].bias[:5] = 0
+    want = float(sum((p != 0).float().sum() for p in model.parameters()) / sum(p.numel() for p in model.parameters()) * 100)
+    assert abs(driver_io.kept_parameter_percentage(model) - want) < 1e-4
