@@ -262,33 +262,46 @@ __device__ __forceinline__ void lt_apply_vec(const LtMat& M, uint32_t row, uint3
   lt_score_bits<DT, AL, false>(M, row, col, r, u, raw);
   const int64_t c0 = (int64_t)col * 8;
   char* wrow = reinterpret_cast<char*>(M.W) + (int64_t)row * M.ld * DType<DT>::kBytes;
-  uint32_t m = 0;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) m |= (u[e] < tcmp ? 1u : 0u) << e;  // padding / NaN patterns are never below tcmp
+  // padding / NaN patterns are never below tcmp.  The packed mask byte is only assembled when somebody wants it.
   if constexpr (AL) {
     if constexpr (DT == ECF_F32) {
+      uint32_t lo4 = 0, hi4 = 0;
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (m >> e & 1) raw[e] = 0;
-      if (m & 0x0fu) stg_v4(wrow + c0 * 4, make_uint4(raw[0], raw[1], raw[2], raw[3]));
-      if (m & 0xf0u) stg_v4(wrow + c0 * 4 + 16, make_uint4(raw[4], raw[5], raw[6], raw[7]));
+      for (int e = 0; e < 8; ++e) {
+        const bool p = u[e] < tcmp;
+        if (p) raw[e] = 0;
+        if (e < 4) lo4 |= p ? 1u : 0u; else hi4 |= p ? 1u : 0u;
+      }
+      if (lo4) stg_v4(wrow + c0 * 4, make_uint4(raw[0], raw[1], raw[2], raw[3]));
+      if (hi4) stg_v4(wrow + c0 * 4 + 16, make_uint4(raw[4], raw[5], raw[6], raw[7]));
       if (M.n_zero != nullptr) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) zeros += (raw[e] & 0x7fffffffu) == 0 ? 1 : 0;
       }
     } else {
+      uint32_t any = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint32_t keep = ((m >> (2 * j) & 1) ? 0u : 0x0000ffffu) | ((m >> (2 * j + 1) & 1) ? 0u : 0xffff0000u);
-        raw[j] &= keep;
+        const uint32_t z = (u[2 * j] < tcmp ? 0x0000ffffu : 0u) | (u[2 * j + 1] < tcmp ? 0xffff0000u : 0u);
+        any |= z;
+        raw[j] &= ~z;
       }
-      if (m) stg_v4(wrow + c0 * 2, make_uint4(raw[0], raw[1], raw[2], raw[3]));
+      if (any) stg_v4(wrow + c0 * 2, make_uint4(raw[0], raw[1], raw[2], raw[3]));
       if (M.n_zero != nullptr) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) zeros += ((raw[j] & 0x00007fffu) == 0 ? 1 : 0) + ((raw[j] & 0x7fff0000u) == 0 ? 1 : 0);
       }
     }
+    if (M.mask != nullptr) {
+      uint32_t m = 0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) m |= (u[e] < tcmp ? 1u : 0u) << e;
+      M.mask[(int64_t)row * M.mask_ld + col] = (uint8_t)m;
+    }
   } else {
+    uint32_t m = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m |= (u[e] < tcmp ? 1u : 0u) << e;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       if (c0 + e < M.C) {
@@ -297,8 +310,8 @@ __device__ __forceinline__ void lt_apply_vec(const LtMat& M, uint32_t row, uint3
         if (M.n_zero != nullptr) zeros += (p || load_elem<DT>(wrow, c0 + e) == 0.f) ? 1 : 0;
       }
     }
+    if (M.mask != nullptr) M.mask[(int64_t)row * M.mask_ld + col] = (uint8_t)m;
   }
-  if (M.mask != nullptr) M.mask[(int64_t)row * M.mask_ld + col] = (uint8_t)m;
 }
 
 // Grid-wide barrier for the co-resident (cooperative) grid.  cooperative_groups' grid.sync() funnels every CTA
