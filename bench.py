@@ -183,9 +183,10 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "calib_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / max(1, len(vals)),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32 scores over fp16/bf16 weights",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": "BLIP-2 (EVA ViT-g + FlanT5-XL) Wanda 50% hot path, 128 samples / 16 batches of 8",
+                   "arithmetic": "fp32 norms and scores over fp16 / bf16 weights and fp32 / fp16 / bf16 hook inputs",
                    "linears": summ["linears"], "params": summ["params"]},
         "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -307,6 +308,9 @@ def run_b200(args):
         launches_per_step += -(-(N_BATCHES * len(pb)) // _abi.SQNORM_MAX_BATCH)  # batched norm launches per block
         launches_per_step += len({(o.W.shape[1], o.W.dtype) for o in pb if o.spec.select == "row"})
         launches_per_step += 1 if any(o.spec.select == "layer" for o in pb) else 0  # batched cooperative select
+
+    if pex is not None:
+        launches_per_step += len(lins)  # one peer-memory exchange kernel per block
 
     def barrier():
         if world > 1:
@@ -556,8 +560,9 @@ def run_b200(args):
         line = {
             "metric": "calib_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "fp32 scores over fp16/bf16 weights", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BLIP-2 (EVA ViT-g + FlanT5-XL) Wanda 50% hot path, 128 samples / 16 batches of 8",
+                       "arithmetic": "fp32 norms and scores over fp16 / bf16 weights and fp32 / fp16 / bf16 hook inputs",
                        "linears": summ["linears"], "params": summ["params"],
                        "algorithmic_bytes_per_step": summ["norm_bytes"] + summ["select_bytes"],
                        "hook_inputs": "q/k/v, wi_0/wi_1 and cross-attention k/v share one input tensor per block as in the model "
