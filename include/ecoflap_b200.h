@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ECF_ABI_VERSION 1
+#define ECF_ABI_VERSION 2 /* 2: batched per-row select, n:m select, peer-memory norm exchange */
 
 #if defined(__GNUC__)
 #define ECF_API __attribute__((visibility("default")))

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in declared if not hasattr(lib, s)]
     assert not missing, f"declared in the header but not exported: {missing}"
     assert sorted(_abi.EXPORTED) == declared, "the ctypes binding and the header disagree"
-    assert _abi.lib.ecf_version() == 1
+    assert _abi.lib.ecf_version() == 2
 
 
 def test_header_cites_the_reference_for_every_entry_point():
