@@ -307,7 +307,12 @@ def run_b200(args):
     for pb in lins:
         launches_per_step += -(-(N_BATCHES * len(pb)) // _abi.SQNORM_MAX_BATCH)  # batched norm launches per block
         launches_per_step += len({(o.W.shape[1], o.W.dtype) for o in pb if o.spec.select == "row"})
-        launches_per_step += 1 if any(o.spec.select == "layer" for o in pb) else 0  # batched cooperative select
+        layer_sel = [o for o in pb if o.spec.select == "layer"]
+        if layer_sel:
+            # per-layer select of the block: split path (sample, count, refine, apply) + the cooperative kernel behind it as
+            # the fallback when every matrix is 16-bit; the cooperative kernel alone otherwise
+            split = os.environ.get("ECF_LT_SPLIT", "1") != "0" and all(o.W.dtype != torch.float32 for o in layer_sel)
+            launches_per_step += 5 if split else 1
 
     if pex is not None:
         launches_per_step += len(lins)  # one peer-memory exchange kernel per block

@@ -604,6 +604,8 @@ struct LtSplit {
   uint32_t* state;      // workspace: per matrix [0] level-0 prefix, [1] nd, [2..3] remaining rank (64 bit)
   unsigned* fill;       // workspace: per warp of the K2 grid, entries in its slice
   uint32_t* lists;      // workspace: [warps][kLtSplitCap]
+  unsigned* ticket;     // workspace: [0] K2 arrivals, [1] K3 arrivals (the last CTA does the serial step of the phase)
+  uint32_t* tkey;       // workspace: per matrix, the threshold key for K4
   unsigned* mini_n;     // workspace: per matrix, exact keys collected for the second digit
   uint32_t* mini;       // workspace: [kLtMaxMat][kLtMiniCap]
 };
@@ -816,6 +818,7 @@ __global__ void __launch_bounds__(kLtThreads, 1) lt_split_sample_kernel(const __
   __shared__ int sh_last;
   if (blockIdx.x == 0 && threadIdx.x == 0) *sp.fallback = 0u;
   if (blockIdx.x == 0 && threadIdx.x < kLtMaxMat) sp.mini_n[threadIdx.x] = 0u;
+  if (blockIdx.x == 0 && threadIdx.x < 2) sp.ticket[threadIdx.x] = 0u;
   lt_phase_sample(b, sh_dyn, sh_scan, sh_range, &sh_last);
 }
 
@@ -875,6 +878,31 @@ __global__ void __launch_bounds__(kLtSplitThreads, 4) lt_split_count_kernel(cons
     if (c) atomicAdd(b.m[tid >> 1].cnt + (tid & 1), c);
   }
   if (tid == 0 && sh_overflow) atomicExch(sp.fallback, 1u);
+  // ---- the last CTA of the grid: bracket check + first-digit search, once, for K3 / K4
+  __shared__ int s_last;
+  __shared__ unsigned long long sh_q[4][4];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(sp.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid < b.n) {
+    const LtMat& M = b.m[tid];
+    const unsigned long long c_lo = __ldcg(M.cnt), c_band = __ldcg(M.cnt + 1), kth = (unsigned long long)M.kth;
+    // the k-th score must lie inside the sampled bracket, and the bracket must resolve in two digits
+    if (!(kth >= c_lo && kth < c_lo + c_band) || sel[tid].nd > 2) atomicExch(sp.fallback, 1u);
+    sel[tid].rem = kth - c_lo;
+  }
+  __syncthreads();
+  lt_find_bins(b, sel, 0, sh_q);
+  if (tid < b.n) {
+    uint32_t* st = sp.state + 4 * tid;
+    st[0] = sel[tid].prefix;
+    st[1] = (uint32_t)sel[tid].nd;
+    st[2] = (uint32_t)sel[tid].rem;
+    st[3] = (uint32_t)(sel[tid].rem >> 32);
+  }
 }
 
 // walk the warp's slice: exact keys of the bracket elements whose first digit is the k-th score's -> the matrix' mini list
@@ -925,66 +953,39 @@ __device__ __forceinline__ void lt_split_collect(const LtBatch& b, const LtSel* 
 }
 
 __global__ void __launch_bounds__(kLtSplitThreads, 4) lt_split_refine_kernel(const __grid_constant__ LtBatch b, const LtSplit sp) {
-  __shared__ unsigned long long sh_q[4][4];
   __shared__ LtSel sel[kLtMaxMat];
-  __shared__ int sh_bad;
-  const int tid = threadIdx.x;
-  const uint32_t gtid = blockIdx.x * kLtSplitThreads + tid, warp = gtid >> 5;
-  if (__ldcg(sp.fallback) != 0u) return;  // uniform: written by the previous kernels only
-  lt_split_load_sel(b, sel);
-  if (tid == 0) sh_bad = 0;
-  __syncthreads();
-  // the k-th score must lie inside the sampled bracket, and the bracket must resolve in two digits
-  if (tid < b.n) {
-    const LtMat& M = b.m[tid];
-    const unsigned long long c_lo = __ldcg(M.cnt), c_band = __ldcg(M.cnt + 1), kth = (unsigned long long)M.kth;
-    if (!(kth >= c_lo && kth < c_lo + c_band) || sel[tid].nd > 2) sh_bad = 1;
-    sel[tid].rem = kth - c_lo;
-  }
-  __syncthreads();
-  if (sh_bad) {
-    if (blockIdx.x == 0 && tid == 0) atomicExch(sp.fallback, 1u);
-    return;
-  }
-  lt_find_bins(b, sel, 0, sh_q);
-  if (blockIdx.x == 0 && tid < b.n) {  // first-digit result for K4
-    uint32_t* st = sp.state + 4 * tid;
-    st[0] = sel[tid].prefix;
-    st[1] = (uint32_t)sel[tid].nd;
-    st[2] = (uint32_t)sel[tid].rem;
-    st[3] = (uint32_t)(sel[tid].rem >> 32);
-  }
-  lt_split_collect(b, sel, sp.lists + (size_t)warp * kLtSplitCap, __ldcg(sp.fill + warp), sp);
-}
-
-__global__ void __launch_bounds__(kLtSplitThreads, 4) lt_split_apply_kernel(const __grid_constant__ LtBatch b, const LtSplit sp) {
-  __shared__ unsigned sh_cnt[kLtMaxMat][2];
   __shared__ unsigned sh_h[kLtBins];
   __shared__ unsigned sh_w[kLtSplitThreads / 32];
-  __shared__ uint32_t sh_tkey[kLtMaxMat];
-  __shared__ LtSel sel[kLtMaxMat];
+  __shared__ int s_last;
   const int tid = threadIdx.x;
-  const uint32_t gthreads = gridDim.x * kLtSplitThreads, gtid = blockIdx.x * kLtSplitThreads + tid;
-  if (__ldcg(sp.fallback) != 0u) return;
+  const uint32_t gtid = blockIdx.x * kLtSplitThreads + tid, warp = gtid >> 5;
+  if (__ldcg(sp.fallback) != 0u) return;  // uniform: final before this kernel starts
   lt_split_load_sel(b, sel);
   __syncthreads();
   if (tid < b.n) {
     const uint32_t* st = sp.state + 4 * tid;
     sel[tid].prefix = __ldcg(st);
     sel[tid].rem = (unsigned long long)__ldcg(st + 2) | ((unsigned long long)__ldcg(st + 3) << 32);
-    sel[tid].done = 1;
-    sh_cnt[tid][0] = 0u;
-    sh_tkey[tid] = 0xffffffffu;
   }
   __syncthreads();
-  // second digit: the k-th score has rank `rem` (0-based) inside the first-digit bucket, whose exact keys K3 collected
-  // (~1000): histogram of their low 11 bits in shared memory, block scan, no further global round trip
+  lt_split_collect(b, sel, sp.lists + (size_t)warp * kLtSplitCap, __ldcg(sp.fill + warp), sp);
+  // ---- the last CTA of the grid: thresholds, once.  Second digit: the k-th score has rank `rem` (0-based) inside the
+  // first-digit bucket, whose exact keys are now complete (~1000): histogram of their low 11 bits in shared memory + scan
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(sp.ticket + 1, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
   for (int mi = 0; mi < b.n; ++mi) {
-    if (sel[mi].nd < 2) continue;  // one digit resolved the key already
+    if (sel[mi].nd < 2) {  // one digit resolved the key already
+      if (tid == 0) sp.tkey[mi] = sel[mi].lo32 + sel[mi].prefix;
+      continue;
+    }
     const unsigned cnt = __ldcg(sp.mini_n + mi);
     if (cnt > (unsigned)kLtMiniCap || cnt == 0u || sel[mi].rem >= (unsigned long long)cnt) {
       // heavy ties inside the bucket (or inconsistent counts): leave the block to the cooperative kernel
-      if (blockIdx.x == 0 && tid == 0) atomicExch(sp.fallback, 1u);
+      if (tid == 0) atomicExch(sp.fallback, 1u);
       return;
     }
     for (int i = tid; i < kLtBins; i += kLtSplitThreads) sh_h[i] = 0u;
@@ -1012,23 +1013,32 @@ __global__ void __launch_bounds__(kLtSplitThreads, 4) lt_split_apply_kernel(cons
     const unsigned rem = (unsigned)sel[mi].rem;
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
-      if (rem >= run && rem < run + loc[j]) sh_tkey[mi] = sel[mi].lo32 + ((sel[mi].prefix << 11) | (uint32_t)(tid * PER + j));
+      if (rem >= run && rem < run + loc[j]) sp.tkey[mi] = sel[mi].lo32 + ((sel[mi].prefix << 11) | (uint32_t)(tid * PER + j));
       run += loc[j];
     }
     __syncthreads();
   }
+}
+
+__global__ void __launch_bounds__(kLtSplitThreads, 4) lt_split_apply_kernel(const __grid_constant__ LtBatch b, const LtSplit sp) {
+  __shared__ unsigned sh_cnt[kLtMaxMat];
+  const int tid = threadIdx.x;
+  const uint32_t gthreads = gridDim.x * kLtSplitThreads, gtid = blockIdx.x * kLtSplitThreads + tid;
+  if (__ldcg(sp.fallback) != 0u) return;  // uniform: final before this kernel starts
+  if (tid < b.n) sh_cnt[tid] = 0u;
+  __syncthreads();
   for (int mi = 0; mi < b.n; ++mi) {
     const LtMat& M = b.m[mi];
-    const uint32_t tkey = sel[mi].nd < 2 ? sel[mi].lo32 + sel[mi].prefix : sh_tkey[mi];
+    const uint32_t tkey = __ldcg(sp.tkey + mi);
     // float semantics of `W_metric <= thres`: NaN scores are never pruned, a NaN threshold prunes nothing
     const uint32_t tcmp = tkey > 0x7f800000u ? 0u : tkey + 1u;
     if (blockIdx.x == 0 && tid == 0 && M.thres_out != nullptr) *M.thres_out = __uint_as_float(tkey);
     if (gtid >= (uint32_t)M.nvec) continue;
-    if (M.dtype == ECF_F16) lt_fast_p5<ECF_F16>(M, tcmp, M.q, gtid, gthreads, &sh_cnt[mi][0]);
-    else lt_fast_p5<ECF_BF16>(M, tcmp, M.q, gtid, gthreads, &sh_cnt[mi][0]);
+    if (M.dtype == ECF_F16) lt_fast_p5<ECF_F16>(M, tcmp, M.q, gtid, gthreads, &sh_cnt[mi]);
+    else lt_fast_p5<ECF_BF16>(M, tcmp, M.q, gtid, gthreads, &sh_cnt[mi]);
   }
   __syncthreads();
-  if (tid < b.n && sh_cnt[tid][0] && b.m[tid].n_zero != nullptr) atomicAdd(b.m[tid].n_zero, (unsigned long long)sh_cnt[tid][0]);
+  if (tid < b.n && sh_cnt[tid] && b.m[tid].n_zero != nullptr) atomicAdd(b.m[tid].n_zero, (unsigned long long)sh_cnt[tid]);
 }
 
 __global__ void __launch_bounds__(kLtThreads, 2) layer_thresh_batched_kernel(const __grid_constant__ LtBatch b) {
@@ -1379,6 +1389,8 @@ extern "C" int ecf_wanda_layer_thresh_apply_batched(const ecf_layer_desc* descs,
   LtSplit sp;
   sp.fallback = reinterpret_cast<unsigned*>(p + 128 + (1 + kLtBarMaxGroups) * 128);
   sp.state = reinterpret_cast<uint32_t*>(p + 128 + (1 + kLtBarMaxGroups) * 128 + 256);
+  sp.ticket = reinterpret_cast<unsigned*>(p + 128 + (1 + kLtBarMaxGroups) * 128 + 64);
+  sp.tkey = reinterpret_cast<uint32_t*>(p + 128 + (1 + kLtBarMaxGroups) * 128 + 128);
   b.fallback = sp.fallback;
   b.after_split = 0;
   p += kLtHeaderBytes;
@@ -1448,8 +1460,8 @@ extern "C" int ecf_wanda_layer_thresh_apply_batched(const ecf_layer_desc* descs,
   // fallback and returns at once when the flag is clear
   bool fast = vec < (1ll << 31);
   for (int i = 0; i < n; ++i) fast = fast && b.m[i].aligned && b.m[i].dtype != ECF_F32 && b.m[i].nvec < (1ll << 29) && b.m[i].nvec >= 1;
-  // ECF_LT_SPLIT=1 enables the split path (off by default until its measurements are in)
-  static const bool split_off = [] { const char* v = getenv("ECF_LT_SPLIT"); return !(v != nullptr && v[0] == '1'); }();
+  // ECF_LT_SPLIT=0 switches the split path off (A/B against the cooperative kernel alone)
+  static const bool split_off = [] { const char* v = getenv("ECF_LT_SPLIT"); return v != nullptr && v[0] == '0'; }();
   if (fast && !split_off) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     static bool attr_done = false;

@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out; O=gpurun_out
-timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_pruners.py -m gpu -x -q -k "layer or vit or lavis or blip" 2>&1 | tail -3
-timeout 100 python tools/one_kernel.py layer_block 0 0 fp16 4 2>&1 | grep "block select" | tail -2
-timeout 200 ncu --clock-control none --metrics gpu__time_duration.sum,launch__registers_per_thread,launch__grid_size,smsp__inst_executed.sum -k regex:"lt_split|layer_thresh" -s 5 -c 5 --csv --log-file $O/lt_split_launches.csv python tools/one_kernel.py layer_block 0 0 fp16 3 > /dev/null 2>&1
+ECF_LT_SPLIT=1 timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_pruners.py -m gpu -x -q -k "layer or vit or lavis or blip" 2>&1 | tail -3
+ECF_LT_SPLIT=1 timeout 100 python tools/one_kernel.py layer_block 0 0 fp16 4 2>&1 | grep "block select" | tail -2
+ECF_LT_SPLIT=1 timeout 200 ncu --clock-control none --metrics gpu__time_duration.sum,launch__registers_per_thread,launch__grid_size,smsp__inst_executed.sum -k regex:"lt_split|layer_thresh" -s 5 -c 5 --csv --log-file $O/lt_split_launches.csv python tools/one_kernel.py layer_block 0 0 fp16 3 > /dev/null 2>&1
 python - <<'PY'
 import csv
 rows=[r for r in csv.reader(l for l in open("gpurun_out/lt_split_launches.csv") if l.startswith('"'))]
