@@ -222,6 +222,15 @@ def layer_thresh_phase_times_us(device) -> list:
     return [(b - a) / 1e3 for a, b in zip(t[:-1], t[1:])]
 
 
+def layer_thresh_last_fallback(device) -> bool:
+    """Test / profiling aid: did the LAST batched per-layer select on ``device`` leave the split path and run the
+    cooperative kernel (k-th score outside the sampled bracket, heavy ties, a full bracket list)?  Synchronises."""
+    torch.cuda.synchronize(device)
+    ws = _ws.get(device, 8192, "layer_thresh")
+    off = 128 + (1 + 32) * 128  # header: phase stamps, barrier lines, then the flag (csrc/layer_thresh.cu)
+    return bool(ws[off:off + 4].view(torch.int32).item() != 0)
+
+
 def layer_thresh_stamps_us(device) -> list:
     """Profiling aid: all 16 %globaltimer stamps of CTA 0 (us, relative to the kernel start; 0 = not taken)."""
     torch.cuda.synchronize(device)

@@ -688,3 +688,28 @@ def test_obs_prune_reference_golden():
         ref = g[f"{name}__Wout"]
         assert ((got == 0) == (ref == 0)).mean() >= 0.995, name
         assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 2e-2, name  # LAPACK (numpy vs torch) differences dominate
+
+
+def test_layer_thresh_split_path_and_its_fallback():
+    """The default path for 16-bit matrices is the four-kernel split path; heavy ties inside the bracket (here: half of the
+    weights identical) make it give the block up to the cooperative kernel.  Both must give the oracle's result."""
+    from ecoflap_b200 import ops
+
+    R, C = 512, 1024
+    s = synth_norm(C, seed=21, outliers=False, dead=False)
+    sd = torch.from_numpy(s).to(dev())
+    W = synth_w(R, C, "fp16", seed=22)
+    Wd = W.clone().to(dev())
+    ops.wanda_layer_thresh_apply(Wd, sd, R * C // 2)
+    assert not ops.layer_thresh_last_fallback(dev())
+    want, _, _ = orc.wanda_prune_layer(f32(W), s, 0.5)
+    assert np.array_equal(f32(Wd), want)
+    Wt = W.clone()
+    Wt[:, ::2] = Wt[0, 0]             # 262 144 equal weights; equal norms below -> one huge tie class around the median
+    st = np.full(C, 0.25, dtype=np.float32)
+    Wd = Wt.clone().to(dev())
+    ops.wanda_layer_thresh_apply(Wd, torch.from_numpy(st).to(dev()), R * C // 2)
+    fell_back = ops.layer_thresh_last_fallback(dev())
+    want, _, _ = orc.wanda_prune_layer(f32(Wt), st, 0.5)
+    assert np.array_equal(f32(Wd), want)
+    assert fell_back, "expected the tie class to overflow the split path's lists"
