@@ -8,7 +8,7 @@
 // A CTA owns a slice of the vector and is independent of the other CTAs:
 //   1. copy the slice of the local vector into the staging half of this call's parity, __threadfence_system()
 //   2. store this call's epoch into flag[cta][my rank] of EVERY peer (remote stores over NVLink)
-//   3. spin until flag[cta][r] >= epoch for every rank r in the local flags
+//   3. spin (bounded) until flag[cta][r] >= epoch for every rank r in the local flags
 //   4. read the slice from every peer's staging half (volatile loads: NVLink, not cached), add in RANK ORDER -- all
 //      ranks compute bit-identical sums -- scale by 1/world, write the local vector in place
 // The epoch lives in device memory (flag[cta][world]) and is advanced by the kernel itself, so a CUDA-graph replay of
@@ -59,12 +59,28 @@ __global__ void __launch_bounds__(kExThreads) norm_exchange_kernel(const __grid_
     volatile unsigned* f = ex_flags(p.peer[tid], p.max_floats) + cta * kExFlagStride + p.rank;
     *f = epoch;
   }
-  // 3. wait for every rank's slice (epochs only grow; wrap-around after 2^32 calls is not handled)
+  // 3. wait for every rank's slice (epochs only grow; wrap-around after 2^32 calls is not handled).  The wait is
+  // bounded (~4 s of SM clocks): a peer that died must not leave this GPU spinning forever -- the slice is then
+  // poisoned with NaN so that the failure is loud downstream instead of a hang or a silently partial mean.
+  __shared__ int s_timeout;
+  if (tid == 0) s_timeout = 0;
+  __syncthreads();
   if (tid < p.world) {
     volatile unsigned* f = my_flags + tid;
-    while ((int)(*f - epoch) < 0) {}
+    const long long t0 = clock64();
+    while ((int)(*f - epoch) < 0) {
+      if (clock64() - t0 > 8000000000ll) {
+        s_timeout = 1;
+        break;
+      }
+    }
   }
   __syncthreads();
+  if (s_timeout) {
+    for (int64_t i = i0 + tid; i < i1; i += kExThreads) p.local[i] = __int_as_float(0x7fffffff);
+    if (tid == 0) my_flags[kExMaxWorld] = epoch;
+    return;
+  }
   __threadfence_system();
   // 4. rank-ordered sum of the peers' slices: all the remote 128-bit loads of a thread are in flight together
   const float inv = 1.0f / (float)p.world;
