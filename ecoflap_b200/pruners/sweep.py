@@ -21,6 +21,7 @@ from typing import Callable, Optional, Sequence
 import torch
 import torch.nn as nn
 
+from .. import dist as edist
 from .. import ops
 from ..accumulators import NormBatch, SparseGPT, WrappedGPT
 
@@ -157,7 +158,14 @@ def sweep_blocks(pruner, model, dataloader, device, spec: SweepSpec, model_prefi
         inps, outs, caches = pruner.prepare_calibration_input_encoder(model, dataloader, device, model_prefix, n_samples,
                                                                      module_to_process)
     n_batches = min(n_samples, len(inps))
+    # P ranks (the reference is single-GPU): the calibration batches are sharded round-robin -- rank r forwards
+    # batches j = r (mod P) through every block -- the block's norms / Hessians are merged by one exchange, and every
+    # rank prunes (Wanda: replicated, identical norms give identical masks; SparseGPT: Linear i on rank i mod P, then a
+    # broadcast of the pruned weights).  A rank only ever reads the activations of its own batches.
+    rank, world = edist.rank_world() if edist.is_dist() else (0, 1)
+    my_batches = list(range(n_batches)) if world == 1 else edist.shard_indices(n_batches, rank, world)
     autocast = spec.autocast or _nullcontext
+    expected_nsamples = spec.expected_nsamples(inps)  # from the catcher's complete list (later lists are per-rank sparse)
     layers = get_module_recursive(model, module_to_process)
     acc_cls = WrappedGPT if method == "wanda" else SparseGPT
 
@@ -185,20 +193,25 @@ def sweep_blocks(pruner, model, dataloader, device, spec: SweepSpec, model_prefi
 
         handles = [subset[name].register_forward_hook(make_hook(name)) for name in wrapped]
         try:
-            for j in range(n_batches):
+            for j in my_batches:
                 with torch.no_grad():
                     with autocast():
                         outs[j] = _run_block(layer, inps[j], caches[j], spec)
             if norm_batch is not None:  # one launch for the whole calibration sweep of this block
                 norm_batch.flush()
+            if world > 1:  # global running means over the batches of all ranks (one all-reduce for the block)
+                if method == "wanda":
+                    edist.sync_block_norms(list(wrapped.values()))
+                else:
+                    edist.sync_block_hessians(list(wrapped.values()))
         finally:
             for h in handles:
                 h.remove()
 
-        layer_items, row_items = [], []
+        layer_items, row_items, obs_owners = [], [], []
         for name in subset:
-            assert wrapped[name].nsamples == spec.expected_nsamples(inps), (
-                f"{name}: accumulated {wrapped[name].nsamples} samples, expected {spec.expected_nsamples(inps)}")
+            assert wrapped[name].nsamples == expected_nsamples, (
+                f"{name}: accumulated {wrapped[name].nsamples} samples, expected {expected_nsamples}")
             print(f"pruning layer {i} name {name}")
             key = spec.sparsity_key(module_to_process, i, name)
             if pruner.prune_n != 0 and method != "wanda":
@@ -218,17 +231,25 @@ def sweep_blocks(pruner, model, dataloader, device, spec: SweepSpec, model_prefi
             elif method == "wanda":
                 wanda_prune_linear(subset[name], wrapped[name], sparsity_ratio[key], spec.select)
             else:
-                wrapped[name].fasterprune(sparsity_ratio[key], prune_n=pruner.prune_n, prune_m=pruner.prune_m,
-                                          percdamp=0.01, blocksize=128)
+                owner = len(obs_owners) % world  # the OBS problems of a block are independent: Linear i on rank i mod P
+                obs_owners.append((name, owner))
+                if owner == rank:
+                    wrapped[name].fasterprune(sparsity_ratio[key], prune_n=pruner.prune_n, prune_m=pruner.prune_m,
+                                              percdamp=0.01, blocksize=128)
                 wrapped[name].free()
         if layer_items:
             ops.wanda_layer_thresh_apply_batched(layer_items)
         if row_items:
             ops.wanda_row_select_apply_batched(row_items)
+        if world > 1:
+            import torch.distributed as dist
+
+            for name, owner in obs_owners:  # every rank continues with the owner's pruned weights
+                dist.broadcast(subset[name].weight.data, src=owner)
         if restore is not None:
             restore()
 
-        for j in range(n_batches):
+        for j in my_batches:
             with torch.no_grad():
                 with autocast():
                     outs[j] = _run_block(layer, inps[j], caches[j], spec)
