@@ -507,3 +507,47 @@ def block_group_name(name, n_fields):
 def count_zero(W):
     """(W == 0).sum() -- wanda_pruner.py:154."""
     return int((np.asarray(W) == 0).sum())
+
+
+# --------------------------------------------------------------------------------------
+# N3  global-pruner baselines (SURVEY section 8f) -- oracle only so far: the CUDA path is a "next" row
+# --------------------------------------------------------------------------------------
+def global_iteration_ratios(target_sparsity, iterations):
+    """p_i = target ** (iterations / i), i = 1..iterations -- global_pruner.py:162-164."""
+    return [float(target_sparsity) ** (iterations / i) for i in range(1, iterations + 1)]
+
+
+def global_get_mask(scores, p, max_sparsity_per_layer):
+    """BLIPT5GlobalPruner.get_mask -- global_pruner.py:116-142.
+
+    ``scores``: ordered dict name -> fp32 array.  Per layer the ``int(numel * (1 - max_sparsity))`` largest scores (and
+    everything tied with the smallest of them, ``>=``) are protected by setting them to finfo.max; then ONE threshold --
+    the ``int(p * total)``-th smallest of all (protected) scores -- keeps ``score > threshold`` everywhere.  Returns
+    (masks as fp32 0/1 arrays, threshold).  ``int(p * total) == 0`` raises like ``threshold[-1]`` on an empty topk."""
+    prot = {}
+    for k, v in scores.items():
+        v = np.array(v, dtype=F32, copy=True)
+        num_to_set = int(v.size * (1 - max_sparsity_per_layer))
+        if num_to_set > 0:
+            t = np.sort(v.reshape(-1), kind="stable")[v.size - num_to_set]  # smallest of the num_to_set largest
+            v[v >= t] = np.finfo(F32).max
+        prot[k] = v
+    allv = np.concatenate([v.reshape(-1) for v in prot.values()])
+    num_to_zero_out = int(p * allv.size)
+    if num_to_zero_out <= 0:
+        raise IndexError("index -1 is out of bounds for dimension 0 with size 0")
+    thres = np.sort(allv, kind="stable")[num_to_zero_out - 1]
+    return {k: (v > thres).astype(F32) for k, v in prot.items()}, thres
+
+
+def global_layerwise_mask(scores, p):
+    """BLIPT5GlobalPruner.get_layerwise_mask -- global_pruner.py:144-157: the same rule per layer, no protection."""
+    masks = {}
+    for k, v in scores.items():
+        v = np.asarray(v, dtype=F32)
+        num_to_zero_out = int(p * v.size)
+        if num_to_zero_out <= 0:
+            raise IndexError("index -1 is out of bounds for dimension 0 with size 0")
+        thres = np.sort(v.reshape(-1), kind="stable")[num_to_zero_out - 1]
+        masks[k] = (v > thres).astype(F32)
+    return masks

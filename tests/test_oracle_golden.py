@@ -164,3 +164,20 @@ def test_nm_select_oracle_matches_the_reference_expression():
                 tmp = W_metric[:, ii:(ii + m)].float()
                 W_mask.scatter_(1, ii + torch.topk(tmp, n, dim=1, largest=False)[1], True)
         assert np.array_equal(orc.nm_select_mask(M, n, m), W_mask.numpy()), (R, C, n, m)
+
+
+def test_global_mask_oracle_matches_the_reference():
+    """N3 (next row): the oracle's restatement of BLIPT5GlobalPruner.get_mask / get_layerwise_mask (global_pruner.py:
+    116-157) against fixtures generated from the unmodified reference class (tests/gen_golden_global.py), including ties
+    and protection of the top (1 - max_sparsity) fraction per layer."""
+    g = np.load("tests/golden/global_mask.npz")
+    names = [str(n) for n in g["names"]]
+    for case in range(4):
+        p, max_sp = float(g[f"c{case}__p"]), float(g[f"c{case}__max_sp"])
+        scores = {n: g[f"c{case}__score{i}"] for i, n in enumerate(names)}
+        masks, _ = orc.global_get_mask(scores, p, max_sp)
+        lw = orc.global_layerwise_mask(scores, p)
+        for i, n in enumerate(names):
+            assert np.array_equal(masks[n], g[f"c{case}__mask{i}"]), (case, n)
+            assert np.array_equal(lw[n], g[f"c{case}__lw{i}"]), (case, n)
+    assert orc.global_iteration_ratios(0.5, 3) == [0.5 ** 3, 0.5 ** 1.5, 0.5]
