@@ -150,8 +150,10 @@ ECF_API int ecf_wanda_layer_thresh_apply(void* W, int w_dtype, int64_t R, int64_
                                  uint8_t* mask_bits, int64_t mask_ld, unsigned long long* n_zero,
                                  void* ws, size_t ws_bytes, ecf_stream_t stream);
 
-/* A3+A5+A7, batched -- the per-layer select of all the Linears of a block (ViT: qkv, proj, fc1, fc2) in ONE
- * cooperative launch; every matrix gets its own exact threshold exactly as in ecf_wanda_layer_thresh_apply
+/* A3+A5+A7, batched -- the per-layer select of all the Linears of a block (ViT: qkv, proj, fc1, fc2) in one call:
+ * four small per-phase kernels for 16-bit aligned matrices with ONE cooperative kernel behind them as the general /
+ * fallback path (fp32, ragged or unaligned matrices, heavy ties); every matrix gets its own exact threshold exactly as in
+ * ecf_wanda_layer_thresh_apply
  * (the reference prunes them one after the other: wanda_pruner.py:536-558).  `descs` is a HOST array of
  * n <= ECF_LAYER_MAX_BATCH distinct matrices.  Workspace: ecf_layer_thresh_batched_workspace_bytes(descs, n),
  * zeroed once before its first use, not shared with other ops or streams. */
