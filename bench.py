@@ -171,6 +171,7 @@ def run_reference(args):
     blocks = wl.blip2_blocks(BATCH)
     threads = os.cpu_count() or 1
     per_step = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    per_step = float(os.environ.get("ECF_REF_STEP_S", per_step))  # tests shrink the bounded CPU sample
     vals, desc = [], ""
     for i in range(args.warmup + args.steps):
         tok, sec, desc = cpu_reference_pass(blocks, N_BATCHES, per_step, threads)
