@@ -20,7 +20,7 @@ EXPORTED = (
     "ecf_version", "ecf_last_error", "ecf_device_sm_count", "ecf_workspace_bytes", "ecf_sqnorm_accum",
     "ecf_sqnorm_batched_workspace_bytes", "ecf_sqnorm_accum_batched",
     "ecf_wanda_row_select_apply", "ecf_wanda_row_select_apply_batched", "ecf_wanda_nm_select_apply", "ecf_wanda_layer_thresh_apply",
-    "ecf_layer_thresh_batched_workspace_bytes", "ecf_wanda_layer_thresh_apply_batched", "ecf_group_reduce_chunk_elems",
+    "ecf_layer_thresh_batched_workspace_bytes", "ecf_layer_thresh_flag_offset", "ecf_wanda_layer_thresh_apply_batched", "ecf_group_reduce_chunk_elems",
     "ecf_norm_exchange_staging_bytes", "ecf_norm_exchange_p2p",
     "ecf_group_abs_reduce", "ecf_zo_perturb", "ecf_count_zero", "ecf_hessian_accum", "ecf_obs_prune",
 )
@@ -81,6 +81,7 @@ def _load():
         "ecf_wanda_nm_select_apply": (i32, [vp, i32, i64, i64, i64, vp, i32, i32, vp, i64, vp, vp]),
         "ecf_wanda_layer_thresh_apply": (i32, [vp, i32, i64, i64, i64, vp, i64, vp, vp, i64, vp, vp, sz, vp]),
         "ecf_layer_thresh_batched_workspace_bytes": (sz, [C.POINTER(LayerDesc), i32]),
+        "ecf_layer_thresh_flag_offset": (sz, []),
         "ecf_wanda_layer_thresh_apply_batched": (i32, [C.POINTER(LayerDesc), i32, vp, sz, vp]),
         "ecf_norm_exchange_staging_bytes": (sz, [i64]),
         "ecf_norm_exchange_p2p": (i32, [vp, i64, C.POINTER(C.c_void_p), i64, i32, i32, vp]),

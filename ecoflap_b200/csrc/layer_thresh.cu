@@ -26,6 +26,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "layer_cut.cuh"
 
 namespace ecf {
 
@@ -581,466 +582,6 @@ __device__ __forceinline__ void lt_phase_sample(const LtBatch& b, unsigned* sh_d
   }
 }
 
-// =====================================================================================================================
-// SPLIT PATH (the common case: every matrix 16-bit and aligned).  The cooperative kernel above pays for its generality:
-// 64 registers x 1024 threads per SM, ~150 instructions per vector and a grid barrier per phase.  Measured stand-alone
-// (tools/micro/lt_micro.cu) a lean count pass needs ~32 registers and streams a 50 MB block in 13 us instead of 27 us.  So
-// the phases become four small kernels (stream order replaces the grid barriers), each with its own register budget:
-//   K1 sample + bracket           (the same lt_phase_sample as above)
-//   K2 count    lean P3 + warp-private bracket lists in GLOBAL memory + walk -> level-0 digit histogram
-//   K3 refine   bracket check, level-0 digit search, walk -> level-1 histogram      (same grid as K2: same list slices)
-//   K4 apply    level-1 digit search -> threshold, lean P5
-// Anything unusual (k-th score outside the sampled bracket, a full list slice, a bracket wider than two digits) raises the
-// fallback flag: K3 / K4 then do nothing and the cooperative kernel, launched behind them, redoes the block from
-// scratch (W is only written by K4).  List entries: matrix << 29 | vector.
-// =====================================================================================================================
-constexpr int kLtSplitThreads = 256;
-constexpr int kLtSplitCap = 256;        // bracket vectors per warp slice (expected ~60)
-constexpr int kLtSplitMaxCtasPerSm = 8;
-constexpr int kLtMiniCap = 8192;        // bracket elements sharing the first digit with the k-th score (expected ~1000)
-
-struct LtSplit {
-  unsigned* fallback;   // workspace: != 0 -> the cooperative kernel does the work
-  uint32_t* state;      // workspace: per matrix [0] level-0 prefix, [1] nd, [2..3] remaining rank (64 bit)
-  unsigned* fill;       // workspace: per warp of the K2 grid, entries in its slice
-  uint32_t* lists;      // workspace: [warps][kLtSplitCap]
-  unsigned* ticket;     // workspace: [0] K2 arrivals, [1] K3 arrivals (the last CTA does the serial step of the phase)
-  uint32_t* tkey;       // workspace: per matrix, the threshold key for K4
-  unsigned* mini_n;     // workspace: per matrix, exact keys collected for the second digit
-  uint32_t* mini;       // workspace: [kLtMaxMat][kLtMiniCap]
-};
-
-template <int DT>
-__device__ __forceinline__ void lt_fast_scores(const uint4& raw, const float* __restrict__ q8, uint32_t (&u)[8]) {
-  const float4 qa = *reinterpret_cast<const float4*>(q8), qb = *reinterpret_cast<const float4*>(q8 + 4);
-  const float q[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
-  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float w0, w1;
-    unpack2<DT>(w[j], w0, w1);
-    u[2 * j] = __float_as_uint(wanda_score(w0, q[2 * j]));
-    u[2 * j + 1] = __float_as_uint(wanda_score(w1, q[2 * j + 1]));
-  }
-}
-
-// count + bracket test of one vector; returns true when it holds a bracket element
-template <int DT>
-__device__ __forceinline__ bool lt_fast_count(const uint4& raw, const float* __restrict__ q8, __half2 pl, __half2 ph, int& pc16) {
-  uint32_t u[8];
-  lt_fast_scores<DT>(raw, q8, u);
-  uint32_t x = 0;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint32_t co = __vminu2(__byte_perm(u[2 * j], u[2 * j + 1], 0x7632) & 0x7fff7fffu, 0x7bff7bffu);
-    const uint32_t ml = __hlt2_mask(lt_h2(co), pl), mh = __hlt2_mask(lt_h2(co), ph);
-    x |= ml ^ mh;
-    pc16 += __popc(ml);
-  }
-  return x != 0;
-}
-
-struct LtFastCur {
-  const char* p;  // address of the current vector
-  uint32_t col;   // its column (in vectors)
-};
-__device__ __forceinline__ void lt_fast_step(LtFastCur& c, uint32_t nvpr, uint32_t sc, int64_t step_bytes, int64_t wrap_bytes) {
-  c.col += sc;
-  c.p += step_bytes;
-  if (c.col >= nvpr) {
-    c.col -= nvpr;
-    c.p += wrap_bytes;
-  }
-}
-
-template <int DT>
-__device__ __forceinline__ void lt_fast_p3(const LtMat& M, int mi, const LtSel& S, const float* __restrict__ qs, uint32_t gtid,
-                                        uint32_t gthreads, uint32_t* __restrict__ my_list, unsigned& fill, unsigned* cnt, int* sh_overflow,
-                                        unsigned* hist) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t lo = S.lo, hi = S.hi;
-  const uint32_t nvpr = (uint32_t)M.nvpr, nvec = (uint32_t)M.nvec;
-  const int64_t ld = M.ld;
-  const uint32_t sr = gthreads / nvpr, sc = gthreads - sr * nvpr;
-  const int64_t step_bytes = ((int64_t)sr * ld + (int64_t)sc * 8) * 2, wrap_bytes = (ld - (int64_t)nvpr * 8) * 2;
-  const __half2 pl = lt_h2(lt_dup(lo)), ph = lt_h2(lt_dup(hi));
-  const uint32_t tag = (uint32_t)mi << 29;
-  LtFastCur a, b2;
-  {
-    const uint32_t v0 = min(gtid, nvec - 1), row = v0 / nvpr;
-    a.col = v0 - row * nvpr;
-    a.p = reinterpret_cast<const char*>(M.W) + ((int64_t)row * ld + (int64_t)a.col * 8) * 2;
-  }
-  int pc16 = 0;
-  unsigned f = fill;
-  for (uint32_t base = gtid - lane; base < nvec; base += 2 * gthreads) {  // warp-uniform trip count
-    const uint32_t va = base + lane, vb = va + gthreads;
-    b2 = a;
-    lt_fast_step(b2, nvpr, sc, step_bytes, wrap_bytes);
-    const bool oka = va < nvec, okb = vb < nvec;
-    uint4 ra = make_uint4(0, 0, 0, 0), rb = ra;
-    if (oka) ra = ldg_noalloc(a.p);
-    if (okb) rb = ldg_noalloc(b2.p);
-    bool ca = false, cb = false;
-    if (oka) ca = lt_fast_count<DT>(ra, qs + a.col * 8, pl, ph, pc16);
-    if (okb) cb = lt_fast_count<DT>(rb, qs + b2.col * 8, pl, ph, pc16);
-    const unsigned bala = __ballot_sync(0xffffffffu, ca), balb = __ballot_sync(0xffffffffu, cb);
-    if (bala | balb) {
-      const unsigned lt = (1u << lane) - 1u;
-      const unsigned posa = f + __popc(bala & lt), posb = f + __popc(bala) + __popc(balb & lt);
-      f += __popc(bala) + __popc(balb);
-      // slice full: give up on the split path (the cooperative kernel redoes the block)
-      if (ca) {
-        if (posa < (unsigned)kLtSplitCap) my_list[posa] = tag | va; else *sh_overflow = 1;
-      }
-      if (cb) {
-        if (posb < (unsigned)kLtSplitCap) my_list[posb] = tag | vb; else *sh_overflow = 1;
-      }
-    }
-    a = b2;
-    lt_fast_step(a, nvpr, sc, step_bytes, wrap_bytes);
-  }
-  fill = min(f, (unsigned)kLtSplitCap);
-  if (pc16) atomicAdd(cnt, (unsigned)pc16 >> 4);
-}
-
-template <int DT>
-__device__ __forceinline__ void lt_fast_apply(char* p, const uint4& raw, const float* __restrict__ q8, uint32_t tcmp, bool count,
-                                              int& zeros, uint8_t* mask_byte) {
-  uint32_t u[8];
-  lt_fast_scores<DT>(raw, q8, u);
-  uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-  uint32_t any = 0;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint32_t m = (u[2 * j] < tcmp ? 0x0000ffffu : 0u) | (u[2 * j + 1] < tcmp ? 0xffff0000u : 0u);
-    any |= m;
-    w[j] &= ~m;
-  }
-  if (any) stg_v4(p, make_uint4(w[0], w[1], w[2], w[3]));
-  if (count) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) zeros += ((w[j] & 0x00007fffu) == 0 ? 1 : 0) + ((w[j] & 0x7fff0000u) == 0 ? 1 : 0);
-  }
-  if (mask_byte != nullptr) {
-    uint32_t pm = 0;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) pm |= (u[e] < tcmp ? 1u : 0u) << e;
-    *mask_byte = (uint8_t)pm;
-  }
-}
-
-template <int DT>
-__device__ __forceinline__ void lt_fast_p5(const LtMat& M, uint32_t tcmp, const float* __restrict__ qs, uint32_t gtid, uint32_t gthreads,
-                                        unsigned* zero_cnt) {
-  const uint32_t nvpr = (uint32_t)M.nvpr, nvec = (uint32_t)M.nvec;
-  const int64_t ld = M.ld;
-  const uint32_t sr = gthreads / nvpr, sc = gthreads - sr * nvpr;
-  const int64_t step_bytes = ((int64_t)sr * ld + (int64_t)sc * 8) * 2, wrap_bytes = (ld - (int64_t)nvpr * 8) * 2;
-  const bool count = M.n_zero != nullptr;
-  uint8_t* const mask = M.mask;
-  const int64_t mask_ld = M.mask_ld;
-  LtFastCur a, b2;
-  uint32_t rowa;
-  {
-    const uint32_t v0 = min(gtid, nvec - 1);
-    rowa = v0 / nvpr;
-    a.col = v0 - rowa * nvpr;
-    a.p = reinterpret_cast<const char*>(M.W) + ((int64_t)rowa * ld + (int64_t)a.col * 8) * 2;
-  }
-  int zeros = 0;
-  for (uint32_t va = gtid; va < nvec; va += 2 * gthreads) {
-    const uint32_t vb = va + gthreads;
-    b2 = a;
-    lt_fast_step(b2, nvpr, sc, step_bytes, wrap_bytes);
-    const bool okb = vb < nvec;
-    const uint4 ra = ldg_noalloc(a.p);
-    uint4 rb = make_uint4(0, 0, 0, 0);
-    if (okb) rb = ldg_noalloc(b2.p);
-    uint8_t *ma = nullptr, *mb = nullptr;
-    if (mask != nullptr) {  // rows only matter for the optional packed mask
-      const uint32_t ra_row = va / nvpr, rb_row = vb / nvpr;
-      ma = mask + (int64_t)ra_row * mask_ld + a.col;
-      mb = mask + (int64_t)rb_row * mask_ld + b2.col;
-    }
-    lt_fast_apply<DT>(const_cast<char*>(a.p), ra, qs + a.col * 8, tcmp, count, zeros, ma);
-    if (okb) lt_fast_apply<DT>(const_cast<char*>(b2.p), rb, qs + b2.col * 8, tcmp, count, zeros, mb);
-    a = b2;
-    lt_fast_step(a, nvpr, sc, step_bytes, wrap_bytes);
-  }
-  if (zeros) atomicAdd(zero_cnt, (unsigned)zeros);
-}
-
-// walk the warp's own list slice: re-read (L2 hit) + exact keys of the bracket vectors, all lanes busy, two in flight
-__device__ __forceinline__ void lt_fast_walk(const LtBatch& b, const LtSel* sel, const uint32_t* __restrict__ my_list, unsigned fill,
-                                             int level, unsigned* sh_hist, unsigned (*sh_cnt)[2]) {
-  const int lane = threadIdx.x & 31;
-  for (unsigned i0 = lane; i0 < fill; i0 += 64) {
-    uint4 r[2];
-    int mi[2];
-    uint32_t col[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const unsigned i = i0 + 32 * k;
-      mi[k] = -1;
-      if (i < fill) {
-        const uint32_t e = my_list[i];
-        const int m = (int)(e >> 29);
-        if (sel[m].nd > level) {
-          const LtMat& M = b.m[m];
-          const uint32_t lv = e & 0x1fffffffu, nvpr = (uint32_t)M.nvpr, row = lv / nvpr;
-          col[k] = lv - row * nvpr;
-          r[k] = ldg_v4(reinterpret_cast<const char*>(M.W) + ((int64_t)row * M.ld + (int64_t)col[k] * 8) * 2);
-          mi[k] = m;
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (mi[k] < 0) continue;
-      const LtMat& M = b.m[mi[k]];
-      uint32_t u[8];
-      const float* q8 = M.q + col[k] * 8;
-      if (M.dtype == ECF_F16) lt_fast_scores<ECF_F16>(r[k], q8, u);
-      else lt_fast_scores<ECF_BF16>(r[k], q8, u);
-      unsigned nb = 0;
-      lt_hist_vec(u, sel[mi[k]], level, sh_hist + mi[k] * kLtBins, nb);
-      if (nb) atomicAdd(&sh_cnt[mi[k]][1], nb);
-    }
-  }
-}
-
-
-__global__ void __launch_bounds__(kLtThreads, 1) lt_split_sample_kernel(const __grid_constant__ LtBatch b, const LtSplit sp) {
-  extern __shared__ unsigned sh_dyn[];
-  __shared__ unsigned long long sh_scan[36];
-  __shared__ unsigned sh_range[2];
-  __shared__ int sh_last;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *sp.fallback = 0u;
-  if (blockIdx.x == 0 && threadIdx.x < kLtMaxMat) sp.mini_n[threadIdx.x] = 0u;
-  if (blockIdx.x == 0 && threadIdx.x < 2) sp.ticket[threadIdx.x] = 0u;
-  lt_phase_sample(b, sh_dyn, sh_scan, sh_range, &sh_last);
-}
-
-// per-CTA select state from the brackets K1 left in global memory
-__device__ __forceinline__ void lt_split_load_sel(const LtBatch& b, LtSel* sel) {
-  for (int mi = threadIdx.x; mi < b.n; mi += blockDim.x) {
-    const LtMat& M = b.m[mi];
-    const uint32_t lo = __ldcg(M.bracket), hi = __ldcg(M.bracket + 1);
-    const uint32_t lo32 = lo << 16;
-    const uint32_t range_hi = (hi >= kLtTop ? 0x80000000u : (hi << 16)) - lo32 - 1u;
-    const int bits = 32 - __clz(range_hi | 1u);
-    sel[mi].lo = lo; sel[mi].hi = hi; sel[mi].lo32 = lo32; sel[mi].range_hi = range_hi;
-    sel[mi].nd = (bits + 10) / 11; sel[mi].prefix = 0; sel[mi].done = 0; sel[mi].active = 1; sel[mi].rem = 0;
-  }
-}
-
-__global__ void __launch_bounds__(kLtSplitThreads, 4) lt_split_count_kernel(const __grid_constant__ LtBatch b, const LtSplit sp) {
-  extern __shared__ unsigned sh_hist[];  // [n][kLtBins]
-  __shared__ unsigned sh_cnt[kLtMaxMat][2];
-  __shared__ LtSel sel[kLtMaxMat];
-  __shared__ int sh_overflow;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const uint32_t gthreads = gridDim.x * kLtSplitThreads, gtid = blockIdx.x * kLtSplitThreads + tid;
-  const uint32_t warp = gtid >> 5;
-  lt_split_load_sel(b, sel);
-  if (tid < b.n * 2) sh_cnt[tid >> 1][tid & 1] = 0u;
-  if (tid == 0) sh_overflow = 0;
-  __syncthreads();
-  // the top digit of a bracket element is at most range_hi >> shift: only those bins (~100) are ever touched
-  for (int mi = 0; mi < b.n; ++mi) {
-    const int used = (int)min((uint32_t)kLtBins, (sel[mi].range_hi >> lt_shift(sel[mi].nd, 0)) + 1u);
-    for (int i = tid; i < used; i += kLtSplitThreads) sh_hist[mi * kLtBins + i] = 0u;
-  }
-  __syncthreads();
-  uint32_t* my_list = sp.lists + (size_t)warp * kLtSplitCap;
-  unsigned fill = 0;
-  for (int mi = 0; mi < b.n; ++mi) {
-    const LtMat& M = b.m[mi];
-    if (M.dtype == ECF_F16)
-      lt_fast_p3<ECF_F16>(M, mi, sel[mi], M.q, gtid, gthreads, my_list, fill, sh_cnt[mi], &sh_overflow, sh_hist + mi * kLtBins);
-    else
-      lt_fast_p3<ECF_BF16>(M, mi, sel[mi], M.q, gtid, gthreads, my_list, fill, sh_cnt[mi], &sh_overflow, sh_hist + mi * kLtBins);
-  }
-  if (lane == 0) sp.fill[warp] = fill;
-  __syncwarp();
-  lt_fast_walk(b, sel, my_list, fill, 0, sh_hist, sh_cnt);
-  __syncthreads();
-  for (int mi = 0; mi < b.n; ++mi) {
-    const int used = (int)min((uint32_t)kLtBins, (sel[mi].range_hi >> lt_shift(sel[mi].nd, 0)) + 1u);
-    for (int i = tid; i < used; i += kLtSplitThreads) {
-      const unsigned c = sh_hist[mi * kLtBins + i];
-      if (c) atomicAdd(b.m[mi].hist + i, c);
-    }
-  }
-  if (tid < b.n * 2) {
-    const unsigned long long c = sh_cnt[tid >> 1][tid & 1];
-    if (c) atomicAdd(b.m[tid >> 1].cnt + (tid & 1), c);
-  }
-  if (tid == 0 && sh_overflow) atomicExch(sp.fallback, 1u);
-  // ---- the last CTA of the grid: bracket check + first-digit search, once, for K3 / K4
-  __shared__ int s_last;
-  __shared__ unsigned long long sh_q[4][4];
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = atomicAdd(sp.ticket, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  if (tid < b.n) {
-    const LtMat& M = b.m[tid];
-    const unsigned long long c_lo = __ldcg(M.cnt), c_band = __ldcg(M.cnt + 1), kth = (unsigned long long)M.kth;
-    // the k-th score must lie inside the sampled bracket, and the bracket must resolve in two digits
-    if (!(kth >= c_lo && kth < c_lo + c_band) || sel[tid].nd > 2) atomicExch(sp.fallback, 1u);
-    sel[tid].rem = kth - c_lo;
-  }
-  __syncthreads();
-  lt_find_bins(b, sel, 0, sh_q);
-  if (tid < b.n) {
-    uint32_t* st = sp.state + 4 * tid;
-    st[0] = sel[tid].prefix;
-    st[1] = (uint32_t)sel[tid].nd;
-    st[2] = (uint32_t)sel[tid].rem;
-    st[3] = (uint32_t)(sel[tid].rem >> 32);
-  }
-}
-
-// walk the warp's slice: exact keys of the bracket elements whose first digit is the k-th score's -> the matrix' mini list
-__device__ __forceinline__ void lt_split_collect(const LtBatch& b, const LtSel* sel, const uint32_t* __restrict__ my_list, unsigned fill,
-                                                 const LtSplit& sp) {
-  const int lane = threadIdx.x & 31;
-  for (unsigned i0 = lane; i0 < fill; i0 += 64) {
-    uint4 r[2];
-    int mi[2];
-    uint32_t col[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const unsigned i = i0 + 32 * k;
-      mi[k] = -1;
-      if (i < fill) {
-        const uint32_t e = my_list[i];
-        const int m = (int)(e >> 29);
-        if (sel[m].nd > 1) {
-          const LtMat& M = b.m[m];
-          const uint32_t lv = e & 0x1fffffffu, nvpr = (uint32_t)M.nvpr, row = lv / nvpr;
-          col[k] = lv - row * nvpr;
-          r[k] = ldg_v4(reinterpret_cast<const char*>(M.W) + ((int64_t)row * M.ld + (int64_t)col[k] * 8) * 2);
-          mi[k] = m;
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (mi[k] < 0) continue;
-      const LtMat& M = b.m[mi[k]];
-      const LtSel& S = sel[mi[k]];
-      uint32_t u[8];
-      const float* q8 = M.q + col[k] * 8;
-      if (M.dtype == ECF_F16) lt_fast_scores<ECF_F16>(r[k], q8, u);
-      else lt_fast_scores<ECF_BF16>(r[k], q8, u);
-      const int sh = lt_shift(S.nd, 0);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const uint32_t key = score_key(__uint_as_float(u[e]));
-        const uint32_t d = key - S.lo32;
-        if (key >= S.lo32 && d <= S.range_hi && (d >> sh) == S.prefix) {
-          const unsigned pos = atomicAdd(sp.mini_n + mi[k], 1u);
-          if (pos < (unsigned)kLtMiniCap) sp.mini[mi[k] * kLtMiniCap + pos] = key;
-        }
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(kLtSplitThreads, 4) lt_split_refine_kernel(const __grid_constant__ LtBatch b, const LtSplit sp) {
-  __shared__ LtSel sel[kLtMaxMat];
-  __shared__ unsigned sh_h[kLtBins];
-  __shared__ unsigned sh_w[kLtSplitThreads / 32];
-  __shared__ int s_last;
-  const int tid = threadIdx.x;
-  const uint32_t gtid = blockIdx.x * kLtSplitThreads + tid, warp = gtid >> 5;
-  if (__ldcg(sp.fallback) != 0u) return;  // uniform: final before this kernel starts
-  lt_split_load_sel(b, sel);
-  __syncthreads();
-  if (tid < b.n) {
-    const uint32_t* st = sp.state + 4 * tid;
-    sel[tid].prefix = __ldcg(st);
-    sel[tid].rem = (unsigned long long)__ldcg(st + 2) | ((unsigned long long)__ldcg(st + 3) << 32);
-  }
-  __syncthreads();
-  lt_split_collect(b, sel, sp.lists + (size_t)warp * kLtSplitCap, __ldcg(sp.fill + warp), sp);
-  // ---- the last CTA of the grid: thresholds, once.  Second digit: the k-th score has rank `rem` (0-based) inside the
-  // first-digit bucket, whose exact keys are now complete (~1000): histogram of their low 11 bits in shared memory + scan
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = atomicAdd(sp.ticket + 1, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int mi = 0; mi < b.n; ++mi) {
-    if (sel[mi].nd < 2) {  // one digit resolved the key already
-      if (tid == 0) sp.tkey[mi] = sel[mi].lo32 + sel[mi].prefix;
-      continue;
-    }
-    const unsigned cnt = __ldcg(sp.mini_n + mi);
-    if (cnt > (unsigned)kLtMiniCap || cnt == 0u || sel[mi].rem >= (unsigned long long)cnt) {
-      // heavy ties inside the bucket (or inconsistent counts): leave the block to the cooperative kernel
-      if (tid == 0) atomicExch(sp.fallback, 1u);
-      return;
-    }
-    for (int i = tid; i < kLtBins; i += kLtSplitThreads) sh_h[i] = 0u;
-    __syncthreads();
-    for (unsigned i = tid; i < cnt; i += kLtSplitThreads)
-      atomicAdd(&sh_h[(__ldcg(sp.mini + (size_t)mi * kLtMiniCap + i) - sel[mi].lo32) & (kLtBins - 1)], 1u);
-    __syncthreads();
-    constexpr int PER = kLtBins / kLtSplitThreads;  // 8 consecutive bins per thread
-    unsigned loc[PER], sum = 0;
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      loc[j] = sh_h[tid * PER + j];
-      sum += loc[j];
-    }
-    unsigned inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
-      if ((tid & 31) >= o) inc += t;
-    }
-    if ((tid & 31) == 31) sh_w[tid >> 5] = inc;
-    __syncthreads();
-    unsigned run = inc - sum;
-    for (int w = 0; w < (tid >> 5); ++w) run += sh_w[w];
-    const unsigned rem = (unsigned)sel[mi].rem;
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      if (rem >= run && rem < run + loc[j]) sp.tkey[mi] = sel[mi].lo32 + ((sel[mi].prefix << 11) | (uint32_t)(tid * PER + j));
-      run += loc[j];
-    }
-    __syncthreads();
-  }
-}
-
-__global__ void __launch_bounds__(kLtSplitThreads, 4) lt_split_apply_kernel(const __grid_constant__ LtBatch b, const LtSplit sp) {
-  __shared__ unsigned sh_cnt[kLtMaxMat];
-  const int tid = threadIdx.x;
-  const uint32_t gthreads = gridDim.x * kLtSplitThreads, gtid = blockIdx.x * kLtSplitThreads + tid;
-  if (__ldcg(sp.fallback) != 0u) return;  // uniform: final before this kernel starts
-  if (tid < b.n) sh_cnt[tid] = 0u;
-  __syncthreads();
-  for (int mi = 0; mi < b.n; ++mi) {
-    const LtMat& M = b.m[mi];
-    const uint32_t tkey = __ldcg(sp.tkey + mi);
-    // float semantics of `W_metric <= thres`: NaN scores are never pruned, a NaN threshold prunes nothing
-    const uint32_t tcmp = tkey > 0x7f800000u ? 0u : tkey + 1u;
-    if (blockIdx.x == 0 && tid == 0 && M.thres_out != nullptr) *M.thres_out = __uint_as_float(tkey);
-    if (gtid >= (uint32_t)M.nvec) continue;
-    if (M.dtype == ECF_F16) lt_fast_p5<ECF_F16>(M, tcmp, M.q, gtid, gthreads, &sh_cnt[mi]);
-    else lt_fast_p5<ECF_BF16>(M, tcmp, M.q, gtid, gthreads, &sh_cnt[mi]);
-  }
-  __syncthreads();
-  if (tid < b.n && sh_cnt[tid] && b.m[tid].n_zero != nullptr) atomicAdd(b.m[tid].n_zero, (unsigned long long)sh_cnt[tid]);
-}
-
 __global__ void __launch_bounds__(kLtThreads, 2) layer_thresh_batched_kernel(const __grid_constant__ LtBatch b) {
   // dynamic shared memory: P1 uses it as the packed sample histogram; afterwards [n][kLtBins] digit histograms followed
   // by the bracket-vector list
@@ -1329,11 +870,12 @@ static size_t lt_mat_fixed_bytes() {
   return align_up((size_t)kLtCoarseBins * 4, 256) + align_up((size_t)3 * kLtBins * 4, 256) + 256 + 256;
 }
 
-static size_t lt_split_bytes() {
-  const size_t warps = (size_t)sm_count() * kLtSplitMaxCtasPerSm * (kLtSplitThreads / 32);
-  return align_up(warps * sizeof(unsigned), 256) + align_up(warps * kLtSplitCap * sizeof(uint32_t), 256) + 256 +
-         align_up((size_t)kLtMaxMat * kLtMiniCap * sizeof(uint32_t), 256);
+static size_t lc_mat_bytes() {
+  // cutoff path, per matrix: bracket histogram, one line of counters / select state / results, the bin list
+  return align_up((size_t)kLcCoarse * kLcCoarseStride * sizeof(unsigned), 256) + 256 + align_up((size_t)kLcListCap * sizeof(uint2), 256);
 }
+
+static size_t lt_split_bytes() { return (size_t)kLtMaxMat * lc_mat_bytes(); }
 
 size_t layer_thresh_batched_workspace_bytes(const ecf_layer_desc* descs, int n) {
   if (descs == nullptr || n < 1 || n > kLtMaxMat) return 0;
@@ -1351,6 +893,8 @@ size_t layer_thresh_workspace_bytes(int64_t R, int64_t C) {
 }
 
 }  // namespace ecf
+
+extern "C" size_t ecf_layer_thresh_flag_offset(void) { return 128 + (1 + ecf::kLtBarMaxGroups) * 128 + 4; }
 
 extern "C" size_t ecf_layer_thresh_batched_workspace_bytes(const ecf_layer_desc* descs, int n) {
   return ecf::layer_thresh_batched_workspace_bytes(descs, n);
@@ -1386,25 +930,20 @@ extern "C" int ecf_wanda_layer_thresh_apply_batched(const ecf_layer_desc* descs,
   b.stamps = reinterpret_cast<unsigned long long*>(p);
   b.bar = reinterpret_cast<unsigned*>(p + 128);  // 128 bytes of stamps, then (1 + kLtBarMaxGroups) 128-byte barrier lines
   static_assert(128 + (1 + kLtBarMaxGroups) * 128 + 256 + kLtMaxMat * 16 <= kLtHeaderBytes, "workspace header too small");
-  LtSplit sp;
-  sp.fallback = reinterpret_cast<unsigned*>(p + 128 + (1 + kLtBarMaxGroups) * 128);
-  sp.state = reinterpret_cast<uint32_t*>(p + 128 + (1 + kLtBarMaxGroups) * 128 + 256);
-  sp.ticket = reinterpret_cast<unsigned*>(p + 128 + (1 + kLtBarMaxGroups) * 128 + 64);
-  sp.tkey = reinterpret_cast<uint32_t*>(p + 128 + (1 + kLtBarMaxGroups) * 128 + 128);
-  b.fallback = sp.fallback;
+  // header words of the cutoff path: [0] fallback flag (live during a launch, cleared by its last kernel),
+  // [1] what it was in the last launch (test / profiling aid), [2] raised inside K1, [16] K1 ticket, [17] K4 ticket
+  unsigned* lc_hdr = reinterpret_cast<unsigned*>(p + 128 + (1 + kLtBarMaxGroups) * 128);
+  b.fallback = lc_hdr;
   b.after_split = 0;
   p += kLtHeaderBytes;
-  {
-    const size_t warps = (size_t)sm_count() * kLtSplitMaxCtasPerSm * (kLtSplitThreads / 32);
-    sp.fill = reinterpret_cast<unsigned*>(p);
-    p += align_up(warps * sizeof(unsigned), 256);
-    sp.lists = reinterpret_cast<uint32_t*>(p);
-    p += align_up(warps * kLtSplitCap * sizeof(uint32_t), 256);
-    sp.mini_n = reinterpret_cast<unsigned*>(p);
-    p += 256;
-    sp.mini = reinterpret_cast<uint32_t*>(p);
-    p += align_up((size_t)kLtMaxMat * kLtMiniCap * sizeof(uint32_t), 256);
-  }
+  char* lc_ws = p;
+  p += (size_t)kLtMaxMat * lc_mat_bytes();
+  LcBatch cb;
+  cb.n = 0;
+  cb.total_ctas = 0;
+  cb.fallback = lc_hdr;
+  cb.ticket = lc_hdr + 16;
+  cb.nsigma = 4.0f;
   int64_t vec = 0, cols = 0;
   for (int i = 0; i < n; ++i) {
     const ecf_layer_desc& d = descs[i];
@@ -1456,44 +995,89 @@ extern "C" int ecf_wanda_layer_thresh_apply_batched(const ecf_layer_desc* descs,
     b.m[i].step_rows = gthreads / b.m[i].nvpr;
     b.m[i].step_cols = gthreads % b.m[i].nvpr;
   }
-  // ---- split path first when every matrix qualifies (16-bit, aligned); the cooperative kernel stays behind it as the
-  // fallback and returns at once when the flag is clear
+  // ---- cutoff path when every matrix qualifies (16-bit, aligned); everything else goes to the cooperative kernel
   bool fast = vec < (1ll << 31);
   for (int i = 0; i < n; ++i) fast = fast && b.m[i].aligned && b.m[i].dtype != ECF_F32 && b.m[i].nvec < (1ll << 29) && b.m[i].nvec >= 1;
-  // ECF_LT_SPLIT=0 switches the split path off (A/B against the cooperative kernel alone)
-  static const bool split_off = [] { const char* v = getenv("ECF_LT_SPLIT"); return v != nullptr && v[0] == '0'; }();
-  if (fast && !split_off) {
+  // ECF_LT_CUT=0 switches the cutoff path off (A/B against the cooperative kernel alone)
+  static const bool cut_off = [] { const char* v = getenv("ECF_LT_CUT"); return v != nullptr && v[0] == '0'; }();
+  // half-width of the sampled bracket in standard deviations of the sample rank (read per call: tests force the exact
+  // fallback with ECF_LT_NSIGMA=0)
+  const char* nsig_env = getenv("ECF_LT_NSIGMA");
+  const float cut_nsigma = nsig_env != nullptr ? (float)atof(nsig_env) : 4.0f;
+  bool cut = fast && !cut_off;
+  for (int i = 0; i < n; ++i)  // 32-bit element indices in the bin list; one dtype per launch (the kernels are specialised)
+    cut = cut && (uint64_t)descs[i].R * (uint64_t)descs[i].C < (1ull << 32) && descs[i].dtype == descs[0].dtype;
+  if (cut) {
+    // ---- cutoff path (layer_cut.cuh): K0 sample, K1 count, K3 apply, K4 fix-up / exact cluster select (fallback)
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    static bool attr_done = false;
-    static int occ_count = 0, occ_apply = 0;
-    const size_t smem_samp = (size_t)kLtSampWords * sizeof(unsigned), smem_hist = (size_t)kLtMaxMat * kLtBins * sizeof(unsigned);
-    if (!attr_done) {
-      ECF_CUDA_OK(cudaFuncSetAttribute(lt_split_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_samp));
-      ECF_CUDA_OK(cudaFuncSetAttribute(lt_split_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_hist));
-      attr_done = true;
+    cb.n = n;
+    cb.nsigma = cut_nsigma;
+    uint64_t units = 0;
+    for (int i = 0; i < n; ++i) {
+      const ecf_layer_desc& d = descs[i];
+      LcMat& M = cb.m[i];
+      M.W = d.W; M.s = d.scaler_row; M.thres_out = d.thres_out; M.mask = d.mask_bits; M.n_zero = d.n_zero;
+      M.ld = d.ld; M.mask_ld = d.mask_ld; M.kth = d.kth_index;
+      M.frac = (double)d.kth_index / ((double)d.R * (double)d.C);
+      M.R = (uint32_t)d.R; M.C = (uint32_t)d.C; M.nvpr = (uint32_t)(d.C / 8); M.dtype = d.dtype;
+      M.slabs = (M.nvpr + kLcSlabVecs - 1) / kLcSlabVecs;
+      units += (uint64_t)M.slabs * M.R;
+      char* q = lc_ws + (size_t)i * lc_mat_bytes();
+      M.hist = reinterpret_cast<unsigned*>(q); q += align_up((size_t)kLcCoarse * kLcCoarseStride * sizeof(unsigned), 256);
+      M.cnt = reinterpret_cast<unsigned long long*>(q);
+      M.sel = reinterpret_cast<int32_t*>(q + 32);
+      M.res = reinterpret_cast<int32_t*>(q + 64);
+      M.list_n = reinterpret_cast<unsigned*>(q + 128);
+      q += 256;
+      M.list = reinterpret_cast<uint2*>(q);
     }
-    const size_t smem_n = (size_t)n * kLtBins * sizeof(unsigned);
-    int oc = 0, oa = 0, orf = 0;
-    ECF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, lt_split_count_kernel, kLtSplitThreads, smem_n));
-    ECF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&orf, lt_split_refine_kernel, kLtSplitThreads, 0));
-    ECF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oa, lt_split_apply_kernel, kLtSplitThreads, 0));
-    occ_count = oc < orf ? oc : orf;
-    occ_apply = oa;
-    if (occ_count > kLtSplitMaxCtasPerSm) occ_count = kLtSplitMaxCtasPerSm;
-    if (occ_apply > kLtSplitMaxCtasPerSm) occ_apply = kLtSplitMaxCtasPerSm;
-    if (occ_count >= 1 && occ_apply >= 1) {
-      int64_t need_ctas = (vec + kLtSplitThreads - 1) / kLtSplitThreads;
-      int64_t g_count = (int64_t)sm_count() * occ_count, g_apply = (int64_t)sm_count() * occ_apply;
-      if (g_count > need_ctas) g_count = need_ctas;
-      if (g_apply > need_ctas) g_apply = need_ctas;
-      const unsigned g_sample = (unsigned)(n * 32);
-      lt_split_sample_kernel<<<g_sample, kLtThreads, smem_samp, st>>>(b, sp);
-      lt_split_count_kernel<<<(unsigned)g_count, kLtSplitThreads, smem_n, st>>>(b, sp);
-      lt_split_refine_kernel<<<(unsigned)g_count, kLtSplitThreads, 0, st>>>(b, sp);
-      lt_split_apply_kernel<<<(unsigned)g_apply, kLtSplitThreads, 0, st>>>(b, sp);
-      ECF_CUDA_OK(cudaGetLastError());
-      b.after_split = 1;
+    const uint64_t g_target = (uint64_t)sm_count() * kLcCtasPerSm;
+    uint64_t rpi = (units + g_target - 1) / g_target;
+    if (rpi < (uint64_t)kLcRowsPerIter) rpi = kLcRowsPerIter;
+    for (;;) {  // the smallest row range per CTA that keeps the grid to one resident wave
+      uint64_t ctas = 0;
+      for (int i = 0; i < n; ++i) ctas += (uint64_t)cb.m[i].slabs * ((cb.m[i].R + rpi - 1) / rpi);
+      if (ctas <= g_target) break;
+      ++rpi;
     }
+    unsigned ctas = 0;
+    for (int i = 0; i < n; ++i) {
+      LcMat& M = cb.m[i];
+      M.rows_per_item = (uint32_t)(rpi < M.R ? rpi : M.R);
+      M.cta_begin = ctas;
+      M.cta_count = M.slabs * (unsigned)((M.R + rpi - 1) / rpi);
+      ctas += M.cta_count;
+    }
+    cb.total_ctas = ctas;
+    static bool lc_attr_done = false;
+    if (!lc_attr_done) {
+      ECF_CUDA_OK(cudaFuncSetAttribute(lc_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLcSampleSmem));
+      lc_attr_done = true;
+    }
+    // ECF_LT_STOP=k (profiling aid): issue only the first k kernels of the chain -- the result is then incomplete
+    const char* stop_env = getenv("ECF_LT_STOP");
+    const int stop = stop_env != nullptr ? atoi(stop_env) : 4;
+    lc_sample_kernel<<<(unsigned)(n * kLcSampleCluster), kLcSampleCtaThreads, kLcSampleSmem, st>>>(cb);
+    if (stop < 2) return ECF_OK;
+    bool extras = false;
+    for (int i = 0; i < n; ++i) extras = extras || descs[i].mask_bits != nullptr || descs[i].n_zero != nullptr;
+    if (descs[0].dtype == ECF_F16) {
+      lc_count_kernel<ECF_F16><<<ctas, kLcThreads, 0, st>>>(cb);
+      if (stop < 3) return ECF_OK;
+      if (extras) lc_apply_kernel<ECF_F16, true><<<ctas, kLcThreads, 0, st>>>(cb);
+      else lc_apply_kernel<ECF_F16, false><<<ctas, kLcThreads, 0, st>>>(cb);
+    } else {
+      lc_count_kernel<ECF_BF16><<<ctas, kLcThreads, 0, st>>>(cb);
+      if (stop < 3) return ECF_OK;
+      if (extras) lc_apply_kernel<ECF_BF16, true><<<ctas, kLcThreads, 0, st>>>(cb);
+      else lc_apply_kernel<ECF_BF16, false><<<ctas, kLcThreads, 0, st>>>(cb);
+    }
+    if (stop < 4) return ECF_OK;
+    ECF_CUDA_OK(cudaGetLastError());
+    // K4: fix-up, or the exact cluster select when the flag is up (one cluster per matrix)
+    lc_finish_kernel<<<(unsigned)(n * kLcCluster), kLcFinishThreads, 0, st>>>(cb);
+    ECF_CUDA_OK(cudaGetLastError());
+    return ECF_OK;
   }
   void* args[] = {(void*)&b};
   ECF_CUDA_OK(cudaLaunchCooperativeKernel((const void*)layer_thresh_batched_kernel, dim3((unsigned)want), dim3(kLtThreads), args, smem,

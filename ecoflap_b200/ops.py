@@ -227,7 +227,7 @@ def layer_thresh_last_fallback(device) -> bool:
     cooperative kernel (k-th score outside the sampled bracket, heavy ties, a full bracket list)?  Synchronises."""
     torch.cuda.synchronize(device)
     ws = _ws.get(device, 8192, "layer_thresh")
-    off = 128 + (1 + 32) * 128  # header: phase stamps, barrier lines, then the flag (csrc/layer_thresh.cu)
+    off = int(lib.ecf_layer_thresh_flag_offset())  # the "flag of the last launch" word of the workspace header
     return bool(ws[off:off + 4].view(torch.int32).item() != 0)
 
 

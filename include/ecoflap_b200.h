@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ECF_ABI_VERSION 2 /* 2: batched per-row select, n:m select, peer-memory norm exchange */
+#define ECF_ABI_VERSION 3 /* 2: batched per-row select, n:m select, peer-memory norm exchange; 3: cutoff-path per-layer select, flag offset */
 
 #if defined(__GNUC__)
 #define ECF_API __attribute__((visibility("default")))
@@ -151,9 +151,9 @@ ECF_API int ecf_wanda_layer_thresh_apply(void* W, int w_dtype, int64_t R, int64_
                                  void* ws, size_t ws_bytes, ecf_stream_t stream);
 
 /* A3+A5+A7, batched -- the per-layer select of all the Linears of a block (ViT: qkv, proj, fc1, fc2) in one call:
- * four small per-phase kernels for 16-bit aligned matrices with ONE cooperative kernel behind them as the general /
- * fallback path (fp32, ragged or unaligned matrices, heavy ties); every matrix gets its own exact threshold exactly as in
- * ecf_wanda_layer_thresh_apply
+ * 16-bit aligned matrices take the cutoff path (sample, count, apply and fix-up kernels working on per-column magnitude
+ * cutoffs, with an exact cluster radix select as its fallback), fp32 / ragged / unaligned matrices ONE cooperative
+ * kernel; every matrix gets its own exact threshold exactly as in ecf_wanda_layer_thresh_apply
  * (the reference prunes them one after the other: wanda_pruner.py:536-558).  `descs` is a HOST array of
  * n <= ECF_LAYER_MAX_BATCH distinct matrices.  Workspace: ecf_layer_thresh_batched_workspace_bytes(descs, n),
  * zeroed once before its first use, not shared with other ops or streams. */
@@ -170,6 +170,10 @@ typedef struct ecf_layer_desc {
   unsigned long long* n_zero; /* nullable: += zero-valued weights after the call */
 } ecf_layer_desc;
 ECF_API size_t ecf_layer_thresh_batched_workspace_bytes(const ecf_layer_desc* descs, int n);
+/* Test / profiling aid: byte offset, inside the per-layer select's workspace, of a 32-bit word that is non-zero when the LAST
+ * launch on that workspace left the sampled cutoff path for the exact cluster radix select (k-th score outside the sampled
+ * bracket, heavy ties, non-finite norms).  Results are exact either way; read the word after synchronising the stream. */
+ECF_API size_t ecf_layer_thresh_flag_offset(void);
 ECF_API int ecf_wanda_layer_thresh_apply_batched(const ecf_layer_desc* descs, int n,
                                          void* ws, size_t ws_bytes, ecf_stream_t stream);
 

@@ -690,26 +690,44 @@ def test_obs_prune_reference_golden():
         assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 2e-2, name  # LAPACK (numpy vs torch) differences dominate
 
 
-def test_layer_thresh_split_path_and_its_fallback():
-    """The default path for 16-bit matrices is the four-kernel split path; heavy ties inside the bracket (here: half of the
-    weights identical) make it give the block up to the cooperative kernel.  Both must give the oracle's result."""
+def test_layer_thresh_cutoff_path_and_its_fallback(monkeypatch):
+    """The default path for 16-bit matrices is the cutoff path (per-column magnitude cutoffs, csrc/layer_cut.cuh); when
+    the k-th score falls outside the sampled bracket -- forced here by a zero-width bracket -- or its bin overflows the
+    list (a huge tie class next to distinct scores), the exact cluster radix select takes over.  All must give the oracle's
+    result."""
     from ecoflap_b200 import ops
 
     R, C = 512, 1024
     s = synth_norm(C, seed=21, outliers=False, dead=False)
     sd = torch.from_numpy(s).to(dev())
+    for dt in ("fp16", "bf16"):
+        W = synth_w(R, C, dt, seed=22)
+        want, mref, thres = orc.wanda_prune_layer(f32(W), s, 0.5)
+        Wd = W.clone().to(dev())
+        ops.wanda_layer_thresh_apply(Wd, sd, R * C // 2)
+        assert not ops.layer_thresh_last_fallback(dev())
+        assert np.array_equal(f32(Wd), want)
+        monkeypatch.setenv("ECF_LT_NSIGMA", "0")
+        Wd = W.clone().to(dev())
+        th = torch.zeros(1, device=dev())
+        mb = ops.alloc_mask_bits(R, C, dev())
+        nz = torch.zeros(1, dtype=torch.int64, device=dev())
+        ops.wanda_layer_thresh_apply(Wd, sd, R * C // 2, thres_out=th, mask_bits=mb, n_zero=nz)
+        monkeypatch.delenv("ECF_LT_NSIGMA")
+        assert ops.layer_thresh_last_fallback(dev()), "a zero-width bracket must miss the k-th score"
+        assert np.array_equal(f32(Wd), want) and float(th.item()) == float(thres)
+        assert np.array_equal(ops.unpack_mask_bits(mb, C).cpu().numpy(), mref) and int(nz.item()) == orc.count_zero(want)
     W = synth_w(R, C, "fp16", seed=22)
-    Wd = W.clone().to(dev())
-    ops.wanda_layer_thresh_apply(Wd, sd, R * C // 2)
-    assert not ops.layer_thresh_last_fallback(dev())
-    want, _, _ = orc.wanda_prune_layer(f32(W), s, 0.5)
-    assert np.array_equal(f32(Wd), want)
     Wt = W.clone()
-    Wt[:, ::2] = Wt[0, 0]             # 262 144 equal weights; equal norms below -> one huge tie class around the median
+    Wt[:, ::2] = Wt[0, 0]             # 262 144 equal weights; equal norms below -> one huge tie class
     st = np.full(C, 0.25, dtype=np.float32)
-    Wd = Wt.clone().to(dev())
-    ops.wanda_layer_thresh_apply(Wd, torch.from_numpy(st).to(dev()), R * C // 2)
-    fell_back = ops.layer_thresh_last_fallback(dev())
-    want, _, _ = orc.wanda_prune_layer(f32(Wt), st, 0.5)
-    assert np.array_equal(f32(Wd), want)
-    assert fell_back, "expected the tie class to overflow the split path's lists"
+    score = np.abs(f32(Wt)) * np.sqrt(st)[None, :]
+    v0 = score[0, 0]
+    below = int((score < v0).sum())
+    for idx in (R * C // 2, below + 10, below - 10, below + 262144 - 5, below + 262144 + 5):
+        Wd = Wt.clone().to(dev())
+        th = torch.zeros(1, device=dev())
+        ops.wanda_layer_thresh_apply(Wd, torch.from_numpy(st).to(dev()), idx, thres_out=th)
+        thres = np.sort(score.flatten())[idx]
+        assert float(th.item()) == float(thres), idx
+        assert np.array_equal(f32(Wd), np.where(score <= thres, 0.0, f32(Wt)).astype(np.float32)), idx
