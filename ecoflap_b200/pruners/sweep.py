@@ -128,7 +128,9 @@ def capture_block_inputs(pruner, model, dataloader, device, spec: SweepSpec, mod
 
 def _run_block(layer, inp, cache, spec):
     out = layer(inp, **cache)
-    if spec.block_output_index is not None:
+    # T5/BERT blocks return tuples; a block that returns a bare tensor (transformers >= 5 LlamaDecoderLayer) must not be
+    # indexed -- out[0] would silently drop the batch dimension
+    if spec.block_output_index is not None and isinstance(out, (tuple, list)):
         out = out[spec.block_output_index]
     return out
 
@@ -184,7 +186,9 @@ def sweep_blocks(pruner, model, dataloader, device, spec: SweepSpec, model_prefi
             permute = restore is not None and not name.startswith("hacky")
 
             def hook(_, inp, out):
-                x = inp[0].data
+                # detach() shares the version counter with the live activation (``.data`` has its own), so that
+                # NormBatch.flush() notices an in-place update between this hook and the deferred launch
+                x = inp[0].detach()
                 if permute:  # CLIP blocks are LND: the MLP hooks see [L, N, D] (CoOp wanda_pruner.py:349-353)
                     x = x.permute(1, 0, 2)
                 wrapped[name].add_batch(x, out.data)

@@ -3,11 +3,12 @@
 (``batch[0].shape[0]`` samples), blocks run without autocast, BERT layers use the per-row select and the ViT
 the per-layer threshold.
 
-Deviation, on purpose: the reference builds ``LayerSparsity(..., self.score_method, self.task, mapping)``
-positionally (wanda_pruner.py:707-717), which binds ``task`` to ``num_noise`` and the mapping to ``noise_eps``
-and leaves ``layer_to_group_mapping`` empty -- ECoFLaP allocation silently degenerates to uniform sparsity in
-that copy.  Here the arguments are passed by keyword so the requested granularity takes effect; pass
-``reference_uniform_quirk=True`` to reproduce the reference's degenerate behaviour exactly.
+Reference quirk, reproduced by default: the reference builds ``LayerSparsity(..., self.score_method, self.task,
+mapping)`` positionally (wanda_pruner.py:707-717), which binds ``task`` to ``num_noise`` and the mapping to
+``noise_eps`` and leaves ``layer_to_group_mapping`` empty -- ECoFLaP allocation silently degenerates to uniform
+sparsity in that copy.  A drop-in must give the reference's result, so ``reference_uniform_quirk=True`` is the default;
+``reference_uniform_quirk=False`` is the opt-in fix (arguments passed by keyword, the requested granularity takes
+effect).
 """
 from __future__ import annotations
 
@@ -93,7 +94,7 @@ class BLIPBertLayerWandaPruner(_UPopBase):
                  keep_indices_or_masks_cache=None, is_strct_pruning=False, num_samples=64, is_global=False,
                  bert_model_prefix="text_encoder", vit_model_prefix="visual_encoder", sparsity_ratio_granularity=None,
                  max_sparsity_per_layer=0.8, score_method="GradMagSquare_avg", num_data_first_stage=128, task="nlvr",
-                 reference_uniform_quirk=False, **kwargs):
+                 reference_uniform_quirk=True, **kwargs):
         super().__init__(model=model, data_loader=data_loader, prune_spec=None, is_strct_pruning=is_strct_pruning,
                          importance_scores_cache=importance_scores_cache,
                          keep_indices_or_masks_cache=keep_indices_or_masks_cache, is_global=is_global,

@@ -1,4 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-ncu --set full --cache-control none --warp-sampling-interval 0 --clock-control none --import-source on -k regex:"lc_" -s 4 -c 4 -o gpurun_out/lc_r2b -f python tools/lt_cut_probe.py vitg fp16 1 > gpurun_out/ncu_lc.log 2>&1
-tail -3 gpurun_out/ncu_lc.log
+python tools/lt_cut_probe.py vitg fp16 5 > gpurun_out/lt_cut_vitg.log 2>&1
+grep -v "thres ok" gpurun_out/lt_cut_vitg.log
+ncu --set full --warp-sampling-interval 0 --clock-control none --import-source on -k regex:"lc_" -s 4 -c 4 -o gpurun_out/lc_r2c -f python tools/lt_cut_probe.py vitg fp16 1 > gpurun_out/ncu_lc.log 2>&1
+tail -2 gpurun_out/ncu_lc.log

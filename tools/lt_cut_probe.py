@@ -66,6 +66,32 @@ for _ in range(reps):
     ts.append(a.elapsed_time(b) * 1e3)
 print(f"   warm L2: best {min(ts):.1f} us")
 
+# clean flush: the write flush leaves L2 full of DIRTY lines whose write-back competes with the kernel's own traffic; a
+# streaming read after it leaves CLEAN lines (what a preceding norm kernel leaves behind in the real sweep)
+scratch2 = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+ts = []
+for _ in range(reps):
+    for w, w0 in zip(Ws, W0):
+        w.copy_(w0)
+    scratch.zero_()
+    scratch2.sum()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); g.replay(); b.record()
+    torch.cuda.synchronize()
+    ts.append(a.elapsed_time(b) * 1e3)
+print(f"   clean flush (write + read): best {min(ts):.1f} us")
+ge = torch.cuda.CUDAGraph()
+tiny = torch.zeros(1, device=dev)
+with torch.cuda.graph(ge):
+    tiny.add_(1)
+ts = []
+for _ in range(reps):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); ge.replay(); b.record()
+    torch.cuda.synchronize()
+    ts.append(a.elapsed_time(b) * 1e3)
+print(f"   (one trivial kernel in a graph, same timing: {min(ts):.1f} us)")
+
 # cumulative chain timing: K0 | K0+K1 | K0+K1+K3 | all four (ECF_LT_STOP is read per call, i.e. at capture time)
 for stop in (1, 2, 3, 4):
     os.environ["ECF_LT_STOP"] = str(stop)
