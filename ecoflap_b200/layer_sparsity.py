@@ -32,6 +32,11 @@ class _UniformSparsity:
 
 
 class LayerSparsity:
+    # Device the zeroth-order noise is drawn on.  None = the parameter's own device, which is what the reference does
+    # (layer_single_base_pruner.py:479: CUDA Philox stream in a GPU run, mt19937 on CPU).  Setting "cpu" draws the
+    # reference's CPU stream and moves z to the parameter -- used to check the loop against CPU-generated fixtures.
+    noise_device = None
+
     def __init__(self, model, data_loader, loss_func, num_samples, original_sparsity, max_sparsity_per_layer=0.8,
                  score_method="GradMagSquare_avg", num_noise=1, noise_eps=1e-3, layer_to_group_mapping={},
                  prune_per_model=False, per_model_group=[]):
@@ -170,7 +175,11 @@ class LayerSparsity:
         (layer_single_base_pruner.py:473-486); the update itself is the ecf_zo_perturb kernel."""
         torch.manual_seed(random_seed)
         for param in params:
-            z = torch.normal(mean=0, std=1, size=param.data.size(), device=param.data.device, dtype=param.data.dtype)
+            if self.noise_device is None:
+                z = torch.normal(mean=0, std=1, size=param.data.size(), device=param.data.device, dtype=param.data.dtype)
+            else:
+                z = torch.normal(mean=0, std=1, size=param.data.size(), device=self.noise_device,
+                                 dtype=param.data.dtype).to(param.data.device)
             data = param.data if param.data.is_contiguous() else param.data.contiguous()
             ops.zo_perturb(data, z, scaling_factor, zo_eps)
             if data is not param.data:

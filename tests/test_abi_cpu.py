@@ -25,7 +25,8 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in declared if not hasattr(lib, s)]
     assert not missing, f"declared in the header but not exported: {missing}"
     assert sorted(_abi.EXPORTED) == declared, "the ctypes binding and the header disagree"
-    assert _abi.lib.ecf_version() == 2
+    header = open(os.path.join(ROOT, "include", "ecoflap_b200.h")).read()
+    assert _abi.lib.ecf_version() == int(re.search(r"#define\s+ECF_ABI_VERSION\s+(\d+)", header).group(1))
 
 
 def test_header_cites_the_reference_for_every_entry_point():

@@ -731,3 +731,78 @@ def test_layer_thresh_cutoff_path_and_its_fallback(monkeypatch):
         thres = np.sort(score.flatten())[idx]
         assert float(th.item()) == float(thres), idx
         assert np.array_equal(f32(Wd), np.where(score <= thres, 0.0, f32(Wt)).astype(np.float32)), idx
+
+
+# ------------------------------------------------------------------------------------------------ A9 prologue
+def _spd_h(C, seed, cond=50.0):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((4 * C, C)).astype(np.float32)
+    X[:, 1] *= 8.0
+    X *= np.linspace(1.0, np.sqrt(cond), C, dtype=np.float32)[None, :]
+    return (2.0 / (4 * C)) * (X.T @ X).astype(np.float32)
+
+
+def _prepare_hinv_gpu(H):
+    from ecoflap_b200.accumulators import SparseGPT
+
+    lin = torch.nn.Linear(H.shape[0], 8, bias=False).to(dev())
+    acc = SparseGPT(lin)
+    acc.H = torch.from_numpy(H.copy()).to(dev())
+    Hinv, dead = acc.prepare_hinv(0.01)
+    return f32(Hinv), dead.cpu().numpy()
+
+
+@pytest.mark.parametrize("variant", ["plain", "dead", "posinf", "neginf", "chol_fails"])
+def test_prepare_hinv_vs_oracle_branches(variant):
+    """SparseGPT.prepare_hinv (cuSOLVER through torch.linalg) against orc.obs_prepare_hinv (sparsegpt_pruner.py:96-163)
+    on the same H, one test per branch of the prologue: dead column (:98-100), +inf / -inf repair (:104-112), and a
+    factorisation that FAILS first and succeeds only after the failure-only damping (:117-131)."""
+    C = 192
+    H = _spd_h(C, seed=5)
+    if variant == "dead":
+        H[7, :] = 0
+        H[:, 7] = 0
+    elif variant == "posinf":
+        H[3, 3] = np.inf
+    elif variant == "neginf":
+        H[5, 9] = H[9, 5] = -np.inf
+    elif variant == "chol_fails":
+        # rank-deficient and slightly indefinite: the first potrf fails, damp = 0.01 * mean(diag) repairs it
+        rng = np.random.default_rng(9)
+        X = rng.standard_normal((C // 2, C)).astype(np.float32)
+        H = (2.0 / (C // 2)) * (X.T @ X).astype(np.float32)
+        H[np.arange(C), np.arange(C)] -= 1e-3 * np.diag(H).mean()
+    want, dead_ref = orc.obs_prepare_hinv(H)
+    got, dead = _prepare_hinv_gpu(H)
+    assert np.array_equal(dead, dead_ref)
+    assert np.all(np.tril(got, -1) == 0), "Hinv must be upper triangular"
+    # Hinv is the upper Cholesky factor of H^-1: compare the factors (1e-3 relative to max |U|, the north_star Hessian
+    # tolerance) and the products U^T U (what the OBS update consumes)
+    scale = np.abs(want).max()
+    tol = 2e-2 if variant == "chol_fails" else 1e-3  # the damped matrix has condition ~1e2/1e-2: LAPACK vs cuSOLVER rounding
+    assert np.abs(got - want).max() <= tol * scale, (variant, np.abs(got - want).max() / scale)
+    if variant == "chol_fails":
+        # the damping step must have been taken exactly as often as in the oracle: diag(U^T U) ~ 1/(lambda + n*damp)
+        P, Pw = got.T @ got, want.T @ want
+        assert np.abs(np.diag(P) - np.diag(Pw)).max() <= 5e-2 * np.abs(np.diag(Pw)).max()
+
+
+def test_prepare_hinv_reference_golden_end_to_end():
+    """fasterprune = prologue + block loop, product vs the reference's pruned weights (tests/golden/obs_prune.npz,
+    incl. the dead-column case), H taken from the fixture so that only A9 + A10 are under test."""
+    from ecoflap_b200.accumulators import SparseGPT
+
+    g = np.load("tests/golden/obs_prune.npz")
+    for name in [str(c) for c in g["cases"]]:
+        dt = str(g[f"{name}__dtype"])
+        W, H, s = g[f"{name}__W"], g[f"{name}__H"], float(g[f"{name}__s"])
+        R, C = W.shape
+        lin = torch.nn.Linear(C, R, bias=False).to(dev()).to(TD[dt])
+        with torch.no_grad():
+            lin.weight.copy_(torch.from_numpy(W).to(dev()))
+        acc = SparseGPT(lin)
+        acc.H = torch.from_numpy(H.copy()).to(dev())
+        acc.fasterprune(s, prune_n=0, prune_m=0, percdamp=0.01, blocksize=128)
+        got, ref = f32(lin.weight.data), g[f"{name}__Wout"]
+        assert ((got == 0) == (ref == 0)).mean() >= 0.995, name
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 2e-2, name

@@ -173,3 +173,72 @@ def test_kept_parameter_percentage_matches_torch():
         model[1].bias[:5] = 0
     want = float(sum((p != 0).float().sum() for p in model.parameters()) / sum(p.numel() for p in model.parameters()) * 100)
     assert abs(driver_io.kept_parameter_percentage(model) - want) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ stage 1 (A12 / A13)
+def _stage1_product(method, noise_device=None):
+    """The product's stage 1 on the device: (per-layer score sums, sparsity dict), same toy BLIP-2 / batches / seeds as
+    tests/gen_golden_stage1.py used with the unmodified reference on CPU."""
+    from ecoflap_b200.compression import load_pruner
+    from ecoflap_b200.layer_sparsity import LayerSparsity
+
+    np.random.seed(42)
+    torch.manual_seed(0)
+    m = cases.blip2_model().cuda()
+    p = load_pruner("blipt5_wanda_pruner", m, cases.blip2_loader(), cfg=dict(
+        t5_prune_spec="2-0.5-1.0-1.0", vit_prune_spec="3-0.5-1.0-1.0", t5_pruning_method="x", vit_pruning_method="x",
+        num_samples=16, sparsity_ratio_granularity="block", max_sparsity_per_layer=0.6, score_method=method,
+        num_data_first_stage=8, num_noise=1, noise_eps=1e-3))
+    rec = {}
+    saved = {fn: getattr(LayerSparsity, fn) for fn in ("compute_importance_scores", "compute_importance_scores_mezo")}
+    old_noise = LayerSparsity.noise_device
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    for fn, orig in saved.items():
+
+        def wrap(self, mapping, _orig=orig):
+            rec["scores"] = _orig(self, mapping)
+            return rec["scores"]
+
+        setattr(LayerSparsity, fn, wrap)
+    try:
+        LayerSparsity.noise_device = noise_device
+        torch.backends.cudnn.allow_tf32 = False  # the patch-embedding conv would otherwise run in TF32
+        p.model_setup_and_record_attributes(m)
+        sd = p.get_sparsity(0.5, sparsity_ratio_granularity="block")
+    finally:
+        LayerSparsity.noise_device = old_noise
+        torch.backends.cudnn.allow_tf32 = old_tf32
+        for fn, orig in saved.items():
+            setattr(LayerSparsity, fn, orig)
+    return {k: float(v.double().sum()) for k, v in rec["scores"].items()}, sd
+
+
+@pytest.mark.parametrize("method", ["GradMagAbs_sum", "GradMagSquare_avg", "GradOnly_sum"])
+def test_first_order_scores_match_reference(method):
+    """A13 (layer_single_base_pruner.py:416-471): mean |dL/dW| (or g^2) over the first-stage batches and the score sums
+    |W||g| / W^2 g / |g| per layer, accumulated on the device here and on CPU fp32 in the reference.  Same fp32 model,
+    batches and autograd; tolerance 1e-3 relative (north_star), ratios to 1e-3 absolute."""
+    g = np.load("tests/golden/stage1_scores.npz")
+    sums, sd = _stage1_product(method)
+    keys = [str(k) for k in g[f"{method}__keys"]]
+    assert list(sd.keys()) == keys
+    got = np.array([sums[k] for k in keys])
+    np.testing.assert_allclose(got, g[f"{method}__sums"], rtol=1e-3, err_msg=method)
+    np.testing.assert_allclose(np.array([sd[k] for k in keys]), g[f"{method}__res"], rtol=0, atol=1e-3, err_msg=method)
+
+
+@pytest.mark.parametrize("method", ["MEZO-GradOnly_sum", "MEZO-GradMagAbs_sum"])
+def test_zeroth_order_loop_matches_reference_on_its_cpu_noise_stream(method):
+    """A12 (layer_single_base_pruner.py:488-561): identical numpy seed stream (np.random.seed(42)), z drawn from the
+    reference's CPU generator and moved to the device (LayerSparsity.noise_device = "cpu"), perturbation by
+    ecf_zo_perturb, fp32 forwards on the GPU.  g-hat = |l+ - l-| / 2e-3 divides fp32 loss rounding (~1e-6 relative
+    between the CPU and GPU forwards) by 2e-3, hence the looser tolerance on the scores; the allocated ratios agree to
+    2e-2 absolute."""
+    g = np.load("tests/golden/stage1_scores.npz")
+    sums, sd = _stage1_product(method, noise_device="cpu")
+    keys = [str(k) for k in g[f"{method}__keys"]]
+    assert list(sd.keys()) == keys
+    got, ref = np.array([sums[k] for k in keys]), g[f"{method}__sums"]
+    np.testing.assert_allclose(got, ref, rtol=5e-2, atol=5e-2 * np.abs(ref).max(), err_msg=method)
+    assert np.corrcoef(got, ref)[0, 1] > 0.999
+    np.testing.assert_allclose(np.array([sd[k] for k in keys]), g[f"{method}__res"], rtol=0, atol=2e-2, err_msg=method)
