@@ -434,6 +434,13 @@ __device__ __forceinline__ void lc_load4(uint4 (&v)[4], const char* p, int64_t s
     else v[u] = make_uint4(kLcNaN2, kLcNaN2, kLcNaN2, kLcNaN2);
   }
 }
+// the same without the range checks (steady state of the streaming loops: four rows, three adds)
+__device__ __forceinline__ void lc_load4_full(uint4 (&v)[4], const char* p, int64_t step, int64_t step2, int64_t step3) {
+  v[0] = ldg_noalloc(p);
+  v[1] = ldg_noalloc(p + step);
+  v[2] = ldg_noalloc(p + step2);
+  v[3] = ldg_noalloc(p + step3);
+}
 
 // column tables of a CTA (shared memory): q = sqrt(scaler_row) and the cutoffs of two keys, for its 128 columns
 struct LcTables {
@@ -536,15 +543,12 @@ __global__ void __launch_bounds__(kLcThreads, kLcCtasPerSm) lc_count_kernel(cons
   const uint32_t cl[4] = {cl4.x, cl4.y, cl4.z, cl4.w}, ch[4] = {ch4.x, ch4.y, ch4.z, ch4.w};
   const uint32_t stash_sa = lc_saddr(S.stash), l16_sa = lc_saddr(S.stash_l16), n_sa = lc_saddr(&S.stash_n), hist_sa = lc_saddr(S.hist);
   const uint32_t spill_sa = lc_saddr(&S.spill[tid]);
-  const unsigned lt_mask = (1u << lane) - 1u;
   unsigned acc = 0, n_in = 0;
-  // both half-warps of a warp must take the same number of trips (the stash append is a warp collective)
-  const int nit_w = __reduce_max_sync(0xffffffffu, I.nit);
-  const char* p = p0;
-  for (int it = 0; it < nit_w; it += 4) {
-    uint4 cu[4] = {nx[0], nx[1], nx[2], nx[3]};
-    p += 4 * step;
-    lc_load4(nx, p, step, it + 4, I.nit);
+  const int64_t step2 = 2 * step, step3 = 3 * step, step4 = 4 * step;
+  // four vectors: count against both cutoffs; vectors holding a bracket element are parked in shared memory (raw bits +
+  // column lane) and finished by the whole CTA after the stream -- no second trip to L2, no dependency chain in the stream.
+  // The append is one shared atomic per lane that has something to park (a quarter of the lanes per step).
+  auto process = [&](const uint4 (&cu)[4]) {
     uint32_t hit4 = 0;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -559,16 +563,8 @@ __global__ void __launch_bounds__(kLcThreads, kLcCtasPerSm) lc_count_kernel(cons
       }
       hit4 |= (x != 0u ? 1u : 0u) << u;
     }
-    // Vectors holding a bracket element are parked in shared memory (raw bits + column lane) and finished by the whole
-    // CTA after the stream: no second trip to L2, no per-thread dependency chain.  One warp-aggregated append per four
-    // vectors: the per-lane counts (0..4) are scanned with three ballots.
-    const int c = __popc(hit4);
-    const unsigned b0 = __ballot_sync(0xffffffffu, c & 1), b1 = __ballot_sync(0xffffffffu, c & 2), b2 = __ballot_sync(0xffffffffu, c & 4);
-    if (b0 | b1 | b2) {
-      const unsigned total = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
-      unsigned pos = 0;
-      if (lane == 0) pos = lc_atom_shared(n_sa, total);
-      pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(b0 & lt_mask) + 2u * __popc(b1 & lt_mask) + 4u * __popc(b2 & lt_mask);
+    if (hit4) {
+      unsigned pos = lc_atom_shared(n_sa, (unsigned)__popc(hit4));
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (hit4 & (1u << u)) {
@@ -583,6 +579,20 @@ __global__ void __launch_bounds__(kLcThreads, kLcCtasPerSm) lc_count_kernel(cons
         }
       }
     }
+  };
+  const char* p = p0;
+  int it = 0;
+  for (; it + 8 <= I.nit; it += 4) {  // steady state: this group and the next are complete
+    uint4 cu[4] = {nx[0], nx[1], nx[2], nx[3]};
+    p += step4;
+    lc_load4_full(nx, p, step, step2, step3);
+    process(cu);
+  }
+  for (; it < I.nit; it += 4) {  // the last one or two groups
+    uint4 cu[4] = {nx[0], nx[1], nx[2], nx[3]};
+    p += step4;
+    lc_load4(nx, p, step, it + 4, I.nit);
+    process(cu);
   }
   __syncthreads();
   const unsigned n_stash = min(S.stash_n, (unsigned)kLcStash);
@@ -680,31 +690,27 @@ __global__ void __launch_bounds__(kLcThreads, kLcCtasPerSm) lc_apply_kernel(cons
   const uint4 ca4 = *reinterpret_cast<const uint4*>(T.ca + l16 * 8), cb4 = *reinterpret_cast<const uint4*>(T.cb + l16 * 8);
   const uint32_t ca[4] = {ca4.x, ca4.y, ca4.z, ca4.w}, cb[4] = {cb4.x, cb4.y, cb4.z, cb4.w};
   // EXTRAS: somebody asked for the zero count or the packed mask (tests, check_sparsity); the plain variant is leaner
-  const bool want_zero = EXTRAS && M.n_zero != nullptr, want_mask = EXTRAS && M.mask != nullptr, bucket = TA != TB;
+  const bool want_zero = EXTRAS && M.n_zero != nullptr, want_mask = EXTRAS && M.mask != nullptr;
   uint8_t* mrow = want_mask ? M.mask + (int64_t)(I.row0 + I.rsub) * M.mask_ld + I.colvec : nullptr;
   const int64_t mstep = (int64_t)kLcRowsPerIter * M.mask_ld;
   const uint32_t q_sa = lc_saddr(T.q + l16 * 8);
   unsigned zacc = 0;
-  const int nit_w = __reduce_max_sync(0xffffffffu, I.nit);  // the list append is a warp collective
-  char* p = p0;
-  for (int it = 0; it < nit_w; it += 4) {
-    uint4 cu[4] = {nx[0], nx[1], nx[2], nx[3]};
-    char* pc = p;
-    p += 4 * step;
-    lc_load4(nx, p, step, it + 4, I.nit);
+  const int64_t step2 = 2 * step, step3 = 3 * step, step4 = 4 * step;
+  // four vectors of this thread's column: zero what lies at or below cutoff A, store; elements between the cutoffs (the k-th
+  // score's bin, ~1 500 per matrix -- one lane in a few thousand vectors) go to the list with their exact keys, one global
+  // reservation per lane that has any.  TA == TB makes the cutoffs equal, so the bin test is empty without a branch.
+  auto process = [&](const uint4 (&cu)[4], char* pc, int it) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       uint32_t w[4] = {cu[u].x, cu[u].y, cu[u].z, cu[u].w};
-      uint32_t xs[4] = {0u, 0u, 0u, 0u};
+      uint32_t xs[4];
       uint32_t x = 0, any = 0, mb = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t a = w[j] & 0x7fff7fffu;
         const uint32_t ma = lc_le2<DT>(a, ca[j]);
-        if (bucket) {
-          xs[j] = ma ^ lc_le2<DT>(a, cb[j]);
-          x |= xs[j];
-        }
+        xs[j] = ma ^ lc_le2<DT>(a, cb[j]);
+        x |= xs[j];
         any |= ma;
         w[j] &= ~ma;
         if (want_zero) zacc = __dp4a(lc_eq0<DT>(w[j]), 0x01010101u, zacc);
@@ -712,20 +718,9 @@ __global__ void __launch_bounds__(kLcThreads, kLcCtasPerSm) lc_apply_kernel(cons
       }
       if (any) stg_v4(pc + (int64_t)u * step, make_uint4(w[0], w[1], w[2], w[3]));
       if (want_mask && it + u < I.nit) mrow[(int64_t)(it + u) * mstep] = (uint8_t)mb;
-      if (__ballot_sync(0xffffffffu, x != 0u)) {
-        // elements inside the k-th score's bin (~1 500 per matrix): exact key -> list for the fix-up, one reservation per warp
+      if (x != 0u) {
         uint32_t bits = lc_bits8(xs);
-        const unsigned c = __popc(bits);
-        unsigned pre = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const unsigned t = __shfl_up_sync(0xffffffffu, pre, o);
-          if (lane >= o) pre += t;
-        }
-        const unsigned total = __shfl_sync(0xffffffffu, pre, 31);
-        unsigned pos = 0;
-        if (lane == 0) pos = atomicAdd(M.list_n, total);
-        pos = __shfl_sync(0xffffffffu, pos, 0) + pre - c;
+        unsigned pos = atomicAdd(M.list_n, (unsigned)__popc(bits));
         const uint32_t row = I.row0 + I.rsub + (uint32_t)(it + u) * kLcRowsPerIter;
         const uint32_t w0[4] = {cu[u].x, cu[u].y, cu[u].z, cu[u].w};
         while (bits) {
@@ -742,6 +737,22 @@ __global__ void __launch_bounds__(kLcThreads, kLcCtasPerSm) lc_apply_kernel(cons
         }
       }
     }
+  };
+  char* p = p0;
+  int it = 0;
+  for (; it + 8 <= I.nit; it += 4) {  // steady state: this group and the next are complete
+    uint4 cu[4] = {nx[0], nx[1], nx[2], nx[3]};
+    char* pc = p;
+    p += step4;
+    lc_load4_full(nx, p, step, step2, step3);
+    process(cu, pc, it);
+  }
+  for (; it < I.nit; it += 4) {  // the last one or two groups (missing rows read as NaN: never below a cutoff, never stored)
+    uint4 cu[4] = {nx[0], nx[1], nx[2], nx[3]};
+    char* pc = p;
+    p += step4;
+    lc_load4(nx, p, step, it + 4, I.nit);
+    process(cu, pc, it);
   }
   if (want_zero) {
     const unsigned z = __reduce_add_sync(0xffffffffu, zacc / 510u);

@@ -57,7 +57,13 @@ class _UPopBase(LayerWiseBasePruner):
         return self.forward_to_cache(model, batch, device)
 
     def _spec_for(self, module_to_process):
-        return _vit_spec() if module_to_process.endswith(".blocks") else _bert_spec()
+        if not module_to_process.endswith(".blocks"):
+            return _bert_spec()
+        spec = _vit_spec()
+        if getattr(self, "task", None) == "nlvr":
+            # the reference asserts twice the count for NLVR's image pairs (UPop wanda_pruner.py:496-497); kept verbatim
+            spec.expected_nsamples = lambda inps: len(inps) * inps[0].shape[0] * 2
+        return spec
 
     def prepare_calibration_input_encoder(self, model, dataloader, device, model_prefix, n_samples,
                                           module_to_process="encoder.block"):

@@ -448,6 +448,179 @@ def clip_forward_to_cache(class_tokens):
     return forward_to_cache
 
 
+# =====================================================================================  LLaMA-style decoder
+class LlamaRMSNorm(nn.Module):
+    def __init__(self, dim, eps=1e-6):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+        self.eps = eps
+
+    def forward(self, x):
+        v = x.float().pow(2).mean(-1, keepdim=True)
+        return (self.weight * (x.float() * torch.rsqrt(v + self.eps))).to(x.dtype)
+
+
+class LlamaDecoderLayer(nn.Module):
+    """``self_attn.{q,k,v,o}_proj`` + ``mlp.{gate,up,down}_proj`` (the names upstream Wanda's LLaMA loop finds).
+    ``tuple_output`` selects the transformers < 5 convention (a tuple) or the >= 5 one (a bare tensor)."""
+
+    def __init__(self, dim, heads, ffn, tuple_output=False):
+        super().__init__()
+        self.heads, self.tuple_output = heads, tuple_output
+        self.input_layernorm = LlamaRMSNorm(dim)
+        self.self_attn = nn.ModuleDict({k: nn.Linear(dim, dim, bias=False) for k in ("q_proj", "k_proj", "v_proj", "o_proj")})
+        self.post_attention_layernorm = LlamaRMSNorm(dim)
+        self.mlp = nn.ModuleDict({"gate_proj": nn.Linear(dim, ffn, bias=False), "up_proj": nn.Linear(dim, ffn, bias=False),
+                                  "down_proj": nn.Linear(ffn, dim, bias=False)})
+
+    def forward(self, hidden_states, attention_mask=None, position_ids=None, **kwargs):
+        B, L, C = hidden_states.shape
+        h = self.input_layernorm(hidden_states)
+        a = self.self_attn
+        q, k, v = (a[n](h).view(B, L, self.heads, -1).transpose(1, 2) for n in ("q_proj", "k_proj", "v_proj"))
+        o = F.scaled_dot_product_attention(q, k, v, is_causal=True).transpose(1, 2).reshape(B, L, C)
+        hidden_states = hidden_states + a["o_proj"](o)
+        h = self.post_attention_layernorm(hidden_states)
+        hidden_states = hidden_states + self.mlp["down_proj"](F.silu(self.mlp["gate_proj"](h)) * self.mlp["up_proj"](h))
+        return (hidden_states,) if self.tuple_output else hidden_states
+
+
+class LlamaModel(nn.Module):
+    """``model.model.layers`` decoder stack, ``model(input_ids, labels=...)`` -> object with ``.loss`` / ``.logits``,
+    ``model.config.use_cache`` (LLaMA/main.py:60-80 duck type)."""
+
+    def __init__(self, vocab=128, dim=64, heads=4, ffn=160, depth=2, tuple_output=False):
+        super().__init__()
+        self.config = SimpleNamespace(use_cache=True, hidden_size=dim)
+        self.model = nn.Module()
+        self.model.embed_tokens = nn.Embedding(vocab, dim)
+        self.model.layers = nn.ModuleList([LlamaDecoderLayer(dim, heads, ffn, tuple_output) for _ in range(depth)])
+        self.model.norm = LlamaRMSNorm(dim)
+        self.lm_head = nn.Linear(dim, vocab, bias=False)
+
+    def forward(self, input_ids, labels=None, **kwargs):
+        x = self.model.embed_tokens(input_ids)
+        pos = torch.arange(input_ids.shape[1], device=input_ids.device).unsqueeze(0)
+        for layer in self.model.layers:
+            out = layer(x, attention_mask=None, position_ids=pos)
+            x = out[0] if isinstance(out, (tuple, list)) else out
+        logits = self.lm_head(self.model.norm(x))
+        loss = None
+        if labels is not None:
+            loss = F.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]).float(), labels[:, 1:].reshape(-1))
+        return SimpleNamespace(loss=loss, logits=logits)
+
+
+def token_batches(n, batch, seq_len, vocab, seed=0):
+    """(input_ids, targets) tuples, the shape upstream Wanda's ``get_loaders`` yields."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n // batch):
+        ids = torch.randint(1, vocab, (batch, seq_len), generator=g)
+        out.append((ids, ids.clone()))
+    return ListLoader(out)
+
+
+# =====================================================================================  BLIP (UPop) NLVR stand-in
+class BlipVitBlock(EvaBlock):
+    """UPop's ViT blocks are called ``blk(x, register_hook)`` (UPop/models/vit.py); the flag is ignored here."""
+
+    def forward(self, x, register_hook=False):
+        return super().forward(x, None)
+
+
+class BertSelfOutput(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.dense = nn.Linear(dim, dim)
+        self.LayerNorm = nn.LayerNorm(dim)
+
+    def forward(self, h, inp):
+        return self.LayerNorm(self.dense(h) + inp)
+
+
+class BertAttention(nn.Module):
+    def __init__(self, dim, heads, kv_dim=None):
+        super().__init__()
+        self.heads = heads
+        kv_dim = kv_dim or dim
+        self.self = nn.ModuleDict({"query": nn.Linear(dim, dim), "key": nn.Linear(kv_dim, dim), "value": nn.Linear(kv_dim, dim)})
+        self.output = BertSelfOutput(dim)
+
+    def forward(self, x, kv=None, mask=None):
+        B, L, C = x.shape
+        kv = x if kv is None else kv
+        q = self.self["query"](x).view(B, L, self.heads, -1).transpose(1, 2)
+        k = self.self["key"](kv).view(B, kv.shape[1], self.heads, -1).transpose(1, 2)
+        v = self.self["value"](kv).view(B, kv.shape[1], self.heads, -1).transpose(1, 2)
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask).transpose(1, 2).reshape(B, L, C)
+        return self.output(o, x)
+
+
+class BertLayer(nn.Module):
+    """BERT layer with cross-attention onto the image tokens; returns a tuple like HF's (UPop/models/med.py)."""
+
+    def __init__(self, dim, heads, ffn):
+        super().__init__()
+        self.attention = BertAttention(dim, heads)
+        self.crossattention = BertAttention(dim, heads)
+        self.intermediate = nn.ModuleDict({"dense": nn.Linear(dim, ffn)})
+        self.output = BertSelfOutput(dim)
+        self.output.dense = nn.Linear(ffn, dim)
+
+    def forward(self, hidden_states, attention_mask=None, head_mask=None, encoder_hidden_states=None,
+                encoder_attention_mask=None, output_attentions=False, mode="multimodal", **kwargs):
+        h = self.attention(hidden_states, mask=attention_mask)
+        if encoder_hidden_states is not None and mode == "multimodal":
+            h = self.crossattention(h, kv=encoder_hidden_states, mask=encoder_attention_mask)
+        return (self.output(F.gelu(self.intermediate["dense"](h)), h),)
+
+
+class BlipCaptionModel(nn.Module):
+    """``visual_encoder.blocks`` + ``text_decoder.bert.encoder.layer``; ``model(image, caption)`` -> LM loss
+    (UPop/models/blip.py duck type used by BLIPBertLayerWandaPruner, task="coco"; ``caption`` is a token tensor here)."""
+
+    def __init__(self, img_size=32, patch=8, dim=64, depth=2, heads=4, mlp_hidden=128, vocab=128, text_depth=2):
+        super().__init__()
+        self.visual_encoder = EvaVisionTransformer(img_size, patch, dim, 0, heads, mlp_hidden)
+        self.visual_encoder.blocks = nn.ModuleList([BlipVitBlock(dim, heads, mlp_hidden) for _ in range(depth)])
+        self.text_decoder = nn.Module()
+        self.text_decoder.config = SimpleNamespace(use_cache=True)
+        self.text_decoder.bert = nn.Module()
+        self.text_decoder.bert.embeddings = nn.Embedding(vocab, dim)
+        self.text_decoder.bert.encoder = nn.Module()
+        self.text_decoder.bert.encoder.layer = nn.ModuleList([BertLayer(dim, heads, mlp_hidden) for _ in range(text_depth)])
+        self.text_decoder.cls = nn.Linear(dim, vocab)
+
+    def encode_image(self, image):
+        ve = self.visual_encoder
+        x = ve.patch_embed(image).flatten(2).transpose(1, 2)
+        x = torch.cat((ve.cls_token.expand(x.shape[0], -1, -1), x), dim=1) + ve.pos_embed
+        for blk in ve.blocks:
+            x = blk(x, False)
+        return ve.norm(x)
+
+    def forward(self, image, caption):
+        enc = self.encode_image(image)
+        caption = caption.to(enc.device)
+        h = self.text_decoder.bert.embeddings(caption)
+        for layer in self.text_decoder.bert.encoder.layer:
+            h = layer(h, attention_mask=None, head_mask=None, encoder_hidden_states=enc, encoder_attention_mask=None,
+                      output_attentions=False, mode="multimodal")[0]
+        logits = self.text_decoder.cls(h)
+        return F.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]).float(), caption[:, 1:].reshape(-1))
+
+
+def caption_batches(n, batch, res, seq_len, vocab, seed=0):
+    """(image, caption, image_id) tuples (UPop coco caption loaders; ``caption`` is a token tensor in this stand-in)."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n // batch):
+        out.append((torch.randn(batch, 3, res, res, generator=g), torch.randint(1, vocab, (batch, seq_len), generator=g),
+                    torch.arange(batch)))
+    return ListLoader(out)
+
+
 # =====================================================================================  synthetic loaders
 class ListLoader:
     """Re-iterable list of batches (the reference re-iterates its calibration loader once per tower and,

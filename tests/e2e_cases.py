@@ -54,3 +54,24 @@ def clip_class_tokens():
 
 def prunable_state(model):
     return {k: v.detach().float().cpu().numpy() for k, v in model.state_dict().items() if v.dim() == 2}
+
+
+def caption_model():
+    torch.manual_seed(0)
+    return syn.init_weights_(syn.BlipCaptionModel(), seed=11).eval()
+
+
+def caption_loader(batch=4, n=16):
+    return syn.caption_batches(n, batch, 32, 6, 128, seed=12)
+
+
+LLAMA_KW = dict(vocab=128, dim=64, heads=4, ffn=160, depth=3)
+
+
+def llama_model(tuple_output=False):
+    torch.manual_seed(0)
+    return syn.init_weights_(syn.LlamaModel(tuple_output=tuple_output, **LLAMA_KW), seed=13).eval()
+
+
+def llama_loader(batch=1, n=16, seq_len=24):
+    return syn.token_batches(n, batch, seq_len, 128, seed=14)

@@ -6,12 +6,16 @@ import csv, io, re, subprocess, sys, collections
 
 rep, cubin, pat = sys.argv[1:4]
 norm = float(sys.argv[4]) if len(sys.argv) > 4 else 1.0
-out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+import os
+kf = os.environ.get('NCU_KERNEL')  # e.g. regex:lc_count -- needed when the report holds several kernels
+out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'] + (['-k', kf, '-c', '1'] if kf else []), capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 h = next(i for i, r in enumerate(rows) if 'Source' in r and 'Address' in r)
 hdr = rows[h]
 ci, si, sm = hdr.index('Instructions Executed'), hdr.index('Source'), hdr.index('# Samples')
-sass = [(r[si].strip(), int(r[ci] or 0), int(r[sm] or 0)) for r in rows[h + 1:] if len(r) > ci]
+body = rows[h + 1:]
+end = next((i for i, r in enumerate(body) if 'Source' in r and 'Address' in r), len(body))  # a second view may follow
+sass = [(r[si].strip(), int(r[ci] or 0), int(r[sm] or 0)) for r in body[:end] if len(r) > ci]
 dis = subprocess.run(['nvdisasm', '-g', '-c', cubin], capture_output=True, text=True).stdout.split('\n')
 # locate the kernel's text section
 start = next(i for i, l in enumerate(dis) if l.startswith('.text.') and pat in l)
