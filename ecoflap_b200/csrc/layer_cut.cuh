@@ -120,6 +120,12 @@ __device__ __forceinline__ uint32_t lc_atom_shared(uint32_t a, uint32_t v) {
   return r;
 }
 
+// programmatic dependent launch (PDL): the four kernels of a block are launched with programmatic stream serialisation, so
+// the next kernel's CTAs become resident -- and run their prologue: ring loads of W, the q table -- while the previous
+// kernel is still finishing; lc_pdl_wait() blocks until the previous kernel has completed and its writes are visible.
+__device__ __forceinline__ void lc_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void lc_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // fp32 value of a 16-bit magnitude pattern
 template <int DT>
 __device__ __forceinline__ float lc_mag(uint32_t m) {
@@ -214,6 +220,7 @@ __global__ void __cluster_dims__(kLcSampleCluster, 1, 1) __launch_bounds__(kLcSa
   __shared__ int s_sh, s_fail, s_lo_none, s_hi_max;
   __shared__ long long s_rlo, s_rhi;
   cg::cluster_group cluster = cg::this_cluster();
+  lc_pdl_trigger();  // K1's CTAs may take the free SMs now: their W loads do not depend on the bracket
   const unsigned rank = cluster.block_rank();
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int mi = (int)blockIdx.x / kLcSampleCluster;
@@ -442,6 +449,30 @@ __device__ __forceinline__ void lc_load4_full(uint4 (&v)[4], const char* p, int6
   v[3] = ldg_noalloc(p + step3);
 }
 
+// ---- asynchronous streaming ring.  A thread's vectors go global -> shared with cp.async (no registers hold data in
+// flight), kRing groups of four rows deep; the thread reads back only its own slots, so the only synchronisation is
+// cp.async.wait_group.  Slot (group, u) of thread t lives at ring + ((group * 4 + u) * kLcThreads + t) * 16: consecutive
+// threads, consecutive 16 bytes -- conflict-free both ways.  With 3-4 CTAs of 256 threads per SM this keeps 100-190 KB per
+// SM in flight (round 2: the register double buffer held 48 KB and the loops were latency bound, ncu long_scoreboard).
+__device__ __forceinline__ void lc_cp16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void lc_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void lc_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr uint32_t kLcSlotStride = kLcThreads * 16u;  // bytes between the slots u and u + 1 of a group
+
+// rows it0 .. it0 + 3 of this thread's column into the group at `group_sa` (missing rows read as NaN pairs), one commit
+__device__ __forceinline__ void lc_issue_group(uint32_t group_sa, const char* p, int64_t step, int it0, int nit) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    if (it0 + u < nit) lc_cp16(group_sa + (uint32_t)u * kLcSlotStride, p + (int64_t)u * step);
+    else lc_sts_v4(group_sa + (uint32_t)u * kLcSlotStride, make_uint4(kLcNaN2, kLcNaN2, kLcNaN2, kLcNaN2));
+  }
+  lc_cp_commit();
+}
+
 // column tables of a CTA (shared memory): q = sqrt(scaler_row) and the cutoffs of two keys, for its 128 columns
 struct LcTables {
   __align__(16) float q[kLcSlabCols];
@@ -475,10 +506,15 @@ __device__ __forceinline__ void lc_tables(const LcMat& M, uint32_t slab, float s
 // ------------------------------------------------------------------------------------------------ K1: count
 constexpr int kLcStash = 1792;  // bracket vectors a CTA parks in shared memory (expected ~20 % of its ~7 000 vectors)
 
+constexpr int kLcRingCount = 2;  // groups in flight per thread in K1 (32 KB of ring next to the 30 KB stash: 3 CTAs per SM)
+constexpr int kLcRingApply = 3;  // ... in K3 (48 KB, 4 CTAs per SM)
+
+constexpr size_t kLcRingCountBytes = (size_t)kLcRingCount * 4 * kLcThreads * 16;
+constexpr size_t kLcRingApplyBytes = (size_t)kLcRingApply * 4 * kLcThreads * 16;
+
 struct LcCountShared {
   LcTables T;
   __align__(16) uint4 stash[kLcStash];
-  __align__(16) uint4 spill[kLcThreads];  // private slots for vectors that do not fit the stash
   uint8_t stash_l16[kLcStash];
   unsigned hist[kLcCoarse];
   unsigned stash_n;
@@ -515,26 +551,39 @@ __device__ __forceinline__ unsigned lc_hist_vec(const uint4& v, uint32_t l16, ui
 
 template <int DT>
 __global__ void __launch_bounds__(kLcThreads, kLcCtasPerSm) lc_count_kernel(const __grid_constant__ LcBatch b) {
+  extern __shared__ __align__(16) uint4 lc_ring[];  // [kLcRingCount][4][kLcThreads]
   __shared__ LcCountShared S;
   static_assert(kLcCoarse == kLcThreads, "one coarse bin per thread");
+  constexpr int G = kLcRingCount;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int l16 = tid & (kLcSlabVecs - 1);
   LcItem I;
   lc_item(b, I);
   const LcMat& M = b.m[I.mi];
-  const int64_t step = (int64_t)kLcRowsPerIter * M.ld * 2;
+  const int64_t step = (int64_t)kLcRowsPerIter * M.ld * 2, step4 = 4 * step;
   const char* p0 = reinterpret_cast<const char*>(M.W) + ((int64_t)(I.row0 + I.rsub) * M.ld + (int64_t)I.colvec * 8) * 2;
-  // everything this CTA needs from memory goes out at once: its first four vectors, the flag, the bracket, its norms
-  uint4 nx[4];
-  lc_load4(nx, p0, step, 0, I.nit);
-  const unsigned flag = *b.fallback;
-  const int4 sel = *reinterpret_cast<const int4*>(M.sel);
+  // everything this CTA needs from memory goes out at once: its first groups of vectors, the flag, the bracket, its norms
+  const uint32_t ring_sa = lc_saddr(lc_ring) + (uint32_t)tid * 16u;
+  const int ngroups = (I.nit + 3) >> 2;
+  const char* pi = p0;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    lc_issue_group(ring_sa + (uint32_t)g * 4u * kLcSlotStride, pi, step, 4 * g, I.nit);
+    pi += step4;
+  }
+  lc_pdl_trigger();
   float sval = 0.f;
   if (tid < kLcSlabCols && I.slab * kLcSlabCols + tid < M.C) sval = M.s[I.slab * kLcSlabCols + tid];
+  lc_pdl_wait();  // K0 is complete: flag, bracket and the cleared counters are visible
+  const unsigned flag = *b.fallback;
+  const int4 sel = *reinterpret_cast<const int4*>(M.sel);
   if (tid < 2) S.cnt[tid] = 0u;
   if (tid == 0) S.stash_n = 0u;
   S.hist[tid] = 0u;
-  if (flag != 0u) return;  // K0 gave the block up (its bracket words are not meaningful then)
+  if (flag != 0u) {  // K0 gave the block up (its bracket words are not meaningful then)
+    lc_cp_wait<0>();
+    return;
+  }
   const int32_t lo = sel.x, hi = sel.y;
   const int shift = sel.z;
   lc_tables<DT>(M, I.slab, sval, lo, hi, S.T, b.fallback + 2);
@@ -542,13 +591,19 @@ __global__ void __launch_bounds__(kLcThreads, kLcCtasPerSm) lc_count_kernel(cons
   const uint4 cl4 = *reinterpret_cast<const uint4*>(S.T.ca + l16 * 8), ch4 = *reinterpret_cast<const uint4*>(S.T.cb + l16 * 8);
   const uint32_t cl[4] = {cl4.x, cl4.y, cl4.z, cl4.w}, ch[4] = {ch4.x, ch4.y, ch4.z, ch4.w};
   const uint32_t stash_sa = lc_saddr(S.stash), l16_sa = lc_saddr(S.stash_l16), n_sa = lc_saddr(&S.stash_n), hist_sa = lc_saddr(S.hist);
-  const uint32_t spill_sa = lc_saddr(&S.spill[tid]);
   unsigned acc = 0, n_in = 0;
-  const int64_t step2 = 2 * step, step3 = 3 * step, step4 = 4 * step;
+  const unsigned lt_mask = (1u << lane) - 1u;
   // four vectors: count against both cutoffs; vectors holding a bracket element are parked in shared memory (raw bits +
   // column lane) and finished by the whole CTA after the stream -- no second trip to L2, no dependency chain in the stream.
-  // The append is one shared atomic per lane that has something to park (a quarter of the lanes per step).
-  auto process = [&](const uint4 (&cu)[4]) {
+  // Both half-warps take the same number of trips (the append is a warp collective; missing rows read as NaN).
+  const int ngroups_w = __reduce_max_sync(0xffffffffu, ngroups);
+  int slot = 0;
+  for (int g = 0; g < ngroups_w; ++g) {
+    lc_cp_wait<G - 1>();
+    const uint32_t gsa = ring_sa + (uint32_t)slot * 4u * kLcSlotStride;
+    uint4 cu[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) cu[u] = lc_lds_v4(gsa + (uint32_t)u * kLcSlotStride);
     uint32_t hit4 = 0;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -563,36 +618,33 @@ __global__ void __launch_bounds__(kLcThreads, kLcCtasPerSm) lc_count_kernel(cons
       }
       hit4 |= (x != 0u ? 1u : 0u) << u;
     }
-    if (hit4) {
-      unsigned pos = lc_atom_shared(n_sa, (unsigned)__popc(hit4));
+    // one warp-aggregated append per four vectors: the per-lane counts (0..4) are scanned with three ballots, one shared
+    // atomic per warp (per-lane atomics on the CTA's single cursor were measured slower: they serialise across 8 warps)
+    const int c = __popc(hit4);
+    const unsigned b0 = __ballot_sync(0xffffffffu, c & 1), b1 = __ballot_sync(0xffffffffu, c & 2), b2 = __ballot_sync(0xffffffffu, c & 4);
+    if (b0 | b1 | b2) {
+      const unsigned total = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
+      unsigned pos = 0;
+      if (lane == 0) pos = lc_atom_shared(n_sa, total);
+      pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(b0 & lt_mask) + 2u * __popc(b1 & lt_mask) + 4u * __popc(b2 & lt_mask);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (hit4 & (1u << u)) {
           if (pos < (unsigned)kLcStash) {
             lc_sts_v4(stash_sa + 16u * pos, cu[u]);
             lc_sts_u8(l16_sa + pos, (uint32_t)l16);
-          } else {  // stash full (heavy ties inside the bracket): finish this vector on the spot, from a private slot
-            lc_sts_v4(spill_sa, cu[u]);
-            n_in += lc_hist_vec<DT>(cu[u], (uint32_t)l16, spill_sa, S.T, hist_sa, lo, shift);
+          } else {  // stash full (heavy ties inside the bracket): finish this vector on the spot, from its ring slot
+            n_in += lc_hist_vec<DT>(cu[u], (uint32_t)l16, gsa + (uint32_t)u * kLcSlotStride, S.T, hist_sa, lo, shift);
           }
           ++pos;
         }
       }
     }
-  };
-  const char* p = p0;
-  int it = 0;
-  for (; it + 8 <= I.nit; it += 4) {  // steady state: this group and the next are complete
-    uint4 cu[4] = {nx[0], nx[1], nx[2], nx[3]};
-    p += step4;
-    lc_load4_full(nx, p, step, step2, step3);
-    process(cu);
-  }
-  for (; it < I.nit; it += 4) {  // the last one or two groups
-    uint4 cu[4] = {nx[0], nx[1], nx[2], nx[3]};
-    p += step4;
-    lc_load4(nx, p, step, it + 4, I.nit);
-    process(cu);
+    // refill the slot just consumed (its contents are in registers / the stash by now) with group g + G
+    if (g + G < ngroups_w) lc_issue_group(gsa, pi, step, 4 * (g + G), I.nit);
+    else lc_cp_commit();  // an empty group keeps wait_group's count in step
+    pi += step4;
+    slot = slot + 1 == G ? 0 : slot + 1;
   }
   __syncthreads();
   const unsigned n_stash = min(S.stash_n, (unsigned)kLcStash);
@@ -666,24 +718,37 @@ __global__ void __launch_bounds__(kLcThreads, kLcCtasPerSm) lc_count_kernel(cons
 
 // ------------------------------------------------------------------------------------------------ K3: apply
 template <int DT, bool EXTRAS>
-__global__ void __launch_bounds__(kLcThreads, kLcCtasPerSm) lc_apply_kernel(const __grid_constant__ LcBatch b) {
+__global__ void __launch_bounds__(kLcThreads, EXTRAS ? 3 : 4) lc_apply_kernel(const __grid_constant__ LcBatch b) {
+  extern __shared__ __align__(16) uint4 lc_ring[];  // [kLcRingApply][4][kLcThreads]
   __shared__ LcTables T;
   __shared__ unsigned sh_zero;
+  constexpr int G = kLcRingApply;
   const int tid = threadIdx.x, lane = tid & 31;
   const int l16 = tid & (kLcSlabVecs - 1);
   LcItem I;
   lc_item(b, I);
   const LcMat& M = b.m[I.mi];
-  const int64_t step = (int64_t)kLcRowsPerIter * M.ld * 2;
+  const int64_t step = (int64_t)kLcRowsPerIter * M.ld * 2, step4 = 4 * step;
   char* p0 = reinterpret_cast<char*>(M.W) + ((int64_t)(I.row0 + I.rsub) * M.ld + (int64_t)I.colvec * 8) * 2;
-  uint4 nx[4];
-  lc_load4(nx, p0, step, 0, I.nit);
-  const unsigned flag = *b.fallback;  // final before this kernel starts
-  const int2 tt = *reinterpret_cast<const int2*>(M.res);
+  const uint32_t ring_sa = lc_saddr(lc_ring) + (uint32_t)tid * 16u;
+  const int ngroups = (I.nit + 3) >> 2;
+  const char* pi = p0;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    lc_issue_group(ring_sa + (uint32_t)g * 4u * kLcSlotStride, pi, step, 4 * g, I.nit);
+    pi += step4;
+  }
+  lc_pdl_trigger();
   float sval = 0.f;
   if (tid < kLcSlabCols && I.slab * kLcSlabCols + tid < M.C) sval = M.s[I.slab * kLcSlabCols + tid];
   if (tid == 0) sh_zero = 0u;
-  if (flag != 0u) return;
+  lc_pdl_wait();  // K1 is complete (it only read W, so the ring loads above were safe to issue early)
+  const unsigned flag = *b.fallback;  // final
+  const int2 tt = *reinterpret_cast<const int2*>(M.res);
+  if (flag != 0u) {
+    lc_cp_wait<0>();
+    return;
+  }
   const int32_t TA = tt.x, TB = tt.y;
   lc_tables<DT>(M, I.slab, sval, TA, TB, T, b.fallback + 2);  // (cannot fire: K1 saw the same norms)
   __syncthreads();
@@ -695,7 +760,6 @@ __global__ void __launch_bounds__(kLcThreads, kLcCtasPerSm) lc_apply_kernel(cons
   const int64_t mstep = (int64_t)kLcRowsPerIter * M.mask_ld;
   const uint32_t q_sa = lc_saddr(T.q + l16 * 8);
   unsigned zacc = 0;
-  const int64_t step2 = 2 * step, step3 = 3 * step, step4 = 4 * step;
   // four vectors of this thread's column: zero what lies at or below cutoff A, store; elements between the cutoffs (the k-th
   // score's bin, ~1 500 per matrix -- one lane in a few thousand vectors) go to the list with their exact keys, one global
   // reservation per lane that has any.  TA == TB makes the cutoffs equal, so the bin test is empty without a branch.
@@ -738,21 +802,20 @@ __global__ void __launch_bounds__(kLcThreads, kLcCtasPerSm) lc_apply_kernel(cons
       }
     }
   };
-  char* p = p0;
-  int it = 0;
-  for (; it + 8 <= I.nit; it += 4) {  // steady state: this group and the next are complete
-    uint4 cu[4] = {nx[0], nx[1], nx[2], nx[3]};
-    char* pc = p;
-    p += step4;
-    lc_load4_full(nx, p, step, step2, step3);
-    process(cu, pc, it);
-  }
-  for (; it < I.nit; it += 4) {  // the last one or two groups (missing rows read as NaN: never below a cutoff, never stored)
-    uint4 cu[4] = {nx[0], nx[1], nx[2], nx[3]};
-    char* pc = p;
-    p += step4;
-    lc_load4(nx, p, step, it + 4, I.nit);
-    process(cu, pc, it);
+  char* pc = p0;
+  int slot = 0;
+  for (int g = 0; g < ngroups; ++g) {
+    lc_cp_wait<G - 1>();
+    const uint32_t gsa = ring_sa + (uint32_t)slot * 4u * kLcSlotStride;
+    uint4 cu[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) cu[u] = lc_lds_v4(gsa + (uint32_t)u * kLcSlotStride);
+    process(cu, pc, 4 * g);  // (missing rows read as NaN: never below a cutoff, never stored)
+    if (g + G < ngroups) lc_issue_group(gsa, pi, step, 4 * (g + G), I.nit);
+    else lc_cp_commit();
+    pi += step4;
+    pc += step4;
+    slot = slot + 1 == G ? 0 : slot + 1;
   }
   if (want_zero) {
     const unsigned z = __reduce_add_sync(0xffffffffu, zacc / 510u);
@@ -982,6 +1045,7 @@ __global__ void __cluster_dims__(kLcCluster, 1, 1) __launch_bounds__(kLcFinishTh
   __shared__ uint32_t sh_sel[2];
   const int mi = (int)blockIdx.x / kLcCluster;
   const LcMat& M = b.m[mi];
+  lc_pdl_wait();  // K3 is complete
   // all the words the fix-up depends on in one round trip
   const unsigned flag = *b.fallback;
   const int4 r0 = *reinterpret_cast<const int4*>(M.res);

@@ -1052,6 +1052,12 @@ extern "C" int ecf_wanda_layer_thresh_apply_batched(const ecf_layer_desc* descs,
     static bool lc_attr_done = false;
     if (!lc_attr_done) {
       ECF_CUDA_OK(cudaFuncSetAttribute(lc_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLcSampleSmem));
+      ECF_CUDA_OK(cudaFuncSetAttribute(lc_count_kernel<ECF_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLcRingCountBytes));
+      ECF_CUDA_OK(cudaFuncSetAttribute(lc_count_kernel<ECF_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLcRingCountBytes));
+      ECF_CUDA_OK(cudaFuncSetAttribute(lc_apply_kernel<ECF_F16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLcRingApplyBytes));
+      ECF_CUDA_OK(cudaFuncSetAttribute(lc_apply_kernel<ECF_F16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLcRingApplyBytes));
+      ECF_CUDA_OK(cudaFuncSetAttribute(lc_apply_kernel<ECF_BF16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLcRingApplyBytes));
+      ECF_CUDA_OK(cudaFuncSetAttribute(lc_apply_kernel<ECF_BF16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLcRingApplyBytes));
       lc_attr_done = true;
     }
     // ECF_LT_STOP=k (profiling aid): issue only the first k kernels of the chain -- the result is then incomplete
@@ -1061,21 +1067,36 @@ extern "C" int ecf_wanda_layer_thresh_apply_batched(const ecf_layer_desc* descs,
     if (stop < 2) return ECF_OK;
     bool extras = false;
     for (int i = 0; i < n; ++i) extras = extras || descs[i].mask_bits != nullptr || descs[i].n_zero != nullptr;
-    if (descs[0].dtype == ECF_F16) {
-      lc_count_kernel<ECF_F16><<<ctas, kLcThreads, 0, st>>>(cb);
-      if (stop < 3) return ECF_OK;
-      if (extras) lc_apply_kernel<ECF_F16, true><<<ctas, kLcThreads, 0, st>>>(cb);
-      else lc_apply_kernel<ECF_F16, false><<<ctas, kLcThreads, 0, st>>>(cb);
-    } else {
-      lc_count_kernel<ECF_BF16><<<ctas, kLcThreads, 0, st>>>(cb);
-      if (stop < 3) return ECF_OK;
-      if (extras) lc_apply_kernel<ECF_BF16, true><<<ctas, kLcThreads, 0, st>>>(cb);
-      else lc_apply_kernel<ECF_BF16, false><<<ctas, kLcThreads, 0, st>>>(cb);
-    }
+    // ECF_LT_PDL=1 launches K1, K3 and K4 with programmatic stream serialisation (PDL, see layer_cut.cuh).  Measured under
+    // CUDA-graph replay (profiles/r2/lt_cut_*_pdl{0,1}.log): no gain -- the graph's kernel-to-kernel gaps are ~1 us already
+    // and the chain is bound by the kernels themselves -- so plain stream order is the default (the griddepcontrol
+    // instructions are no-ops then).
+    static const bool pdl = [] { const char* v = getenv("ECF_LT_PDL"); return v != nullptr && v[0] == '1'; }();
+    auto launch = [&](auto kern, unsigned grid, unsigned block, size_t smem_bytes) -> cudaError_t {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid);
+      cfg.blockDim = dim3(block);
+      cfg.dynamicSmemBytes = smem_bytes;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = pdl ? 1 : 0;
+      return cudaLaunchKernelEx(&cfg, kern, cb);
+    };
+    const bool f16 = descs[0].dtype == ECF_F16;
+    ECF_CUDA_OK(f16 ? launch(lc_count_kernel<ECF_F16>, ctas, kLcThreads, kLcRingCountBytes)
+                    : launch(lc_count_kernel<ECF_BF16>, ctas, kLcThreads, kLcRingCountBytes));
+    if (stop < 3) return ECF_OK;
+    if (f16) ECF_CUDA_OK(extras ? launch(lc_apply_kernel<ECF_F16, true>, ctas, kLcThreads, kLcRingApplyBytes)
+                                : launch(lc_apply_kernel<ECF_F16, false>, ctas, kLcThreads, kLcRingApplyBytes));
+    else ECF_CUDA_OK(extras ? launch(lc_apply_kernel<ECF_BF16, true>, ctas, kLcThreads, kLcRingApplyBytes)
+                            : launch(lc_apply_kernel<ECF_BF16, false>, ctas, kLcThreads, kLcRingApplyBytes));
     if (stop < 4) return ECF_OK;
     ECF_CUDA_OK(cudaGetLastError());
     // K4: fix-up, or the exact cluster select when the flag is up (one cluster per matrix)
-    lc_finish_kernel<<<(unsigned)(n * kLcCluster), kLcFinishThreads, 0, st>>>(cb);
+    ECF_CUDA_OK(launch(lc_finish_kernel, (unsigned)(n * kLcCluster), kLcFinishThreads, 0));
     ECF_CUDA_OK(cudaGetLastError());
     return ECF_OK;
   }
