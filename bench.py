@@ -49,6 +49,11 @@ def parse():
     ap.add_argument("--cpu-sample-s", type=float, default=15.0, help="target seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--prune-wall", default=os.environ.get("ECF_BENCH_PRUNE_WALL", "wanda,sparsegpt,ecoflap"),
+                    help="comma list of full-size BLIP-2 prune() runs to time (wanda, sparsegpt, ecoflap) or 'none'; "
+                         "ecoflap = 4 704 BLIP-2 forwards, ~3 min on one B200")
+    ap.add_argument("--no-sparsegpt-kernels", action="store_true")
+    ap.add_argument("--no-aten", action="store_true")
     return ap.parse_args()
 
 
@@ -105,22 +110,26 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_reference_pass(blocks, n_batches, budget_s, threads):
-    """The reference's path on the host: numpy / plain-C(OpenMP) oracle over as many blocks of the workload as
-    fit in ~budget_s (at least one block of every tower).  Returns (tokens, seconds, description)."""
+    """The reference's path on the host: the plain-C (OpenMP) oracle port over a bounded sample of the workload -- blocks are
+    taken round-robin over the three towers until ~budget_s of CPU work is done (at least one block of every tower) -- and
+    extrapolated to the whole workload WITH THE WORKLOAD'S TOWER MIX (39 ViT-g : 24 T5-encoder : 24 T5-decoder blocks):
+    seconds(workload) = sum over towers of blocks(tower) * mean seconds per sampled block of that tower.
+    Returns (tokens of the whole workload, estimated seconds for it, description)."""
     import numpy as np
 
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import c_oracle
     import ecoflap_oracle as orc
 
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    os.environ["OMP_NUM_THREADS"] = str(threads)  # torchrun exports OMP_NUM_THREADS=1 to its workers
+    used_threads = c_oracle.set_threads(threads)
     rng = np.random.default_rng(0)
     towers = {}
     for b in blocks:
         towers.setdefault(b.name.rsplit(".", 1)[0], []).append(b)
     order = []
     depth = 0
-    while True:  # round-robin over the towers so the sample has the workload's mix
+    while True:
         added = False
         for t in towers.values():
             if depth < len(t):
@@ -129,12 +138,13 @@ def cpu_reference_pass(blocks, n_batches, budget_s, threads):
         if not added:
             break
         depth += 1
-    tokens, t_total, used = 0, 0.0, []
+    t_total, used = 0.0, []
+    per_tower = {k: [0.0, 0] for k in towers}  # seconds, blocks sampled
     cache = {}
     for blk in order:
-        if t_total >= budget_s and len(used) >= len(towers):
+        if t_total >= budget_s and all(v[1] > 0 for v in per_tower.values()):
             break
-        t0 = time.perf_counter()
+        t_blk = 0.0
         for l in blk.linears:
             key = (l.tokens, l.cols, l.x_dtype)
             if key not in cache:
@@ -154,12 +164,18 @@ def cpu_reference_pass(blocks, n_batches, budget_s, threads):
                 c_oracle.wanda_row_prune(W, l.w_dtype, s, orc.row_k(l.cols, SPARSITY))
             else:
                 c_oracle.wanda_layer_prune(W, l.w_dtype, s, orc.layer_kth_index(l.rows * l.cols, SPARSITY))
-            t_total += time.perf_counter() - t1
-            tokens += l.tokens * n_batches
+            t_blk += time.perf_counter() - t1
+        t_total += t_blk
+        tw = per_tower[blk.name.rsplit(".", 1)[0]]
+        tw[0] += t_blk
+        tw[1] += 1
         used.append(blk.name)
-        _ = t0
-    desc = f"{len(used)} of {len(blocks)} blocks ({', '.join(used[:3])}{', ...' if len(used) > 3 else ''}); all Linears, {n_batches} batches of {BATCH}"
-    return tokens, t_total, desc
+    est = sum(len(towers[k]) * v[0] / v[1] for k, v in per_tower.items())
+    tokens = sum(l.tokens * n_batches for b in blocks for l in b.linears)
+    mix = ", ".join(f"{v[1]} of {len(towers[k])} {k.split('.')[-2] if '.' in k else k}" for k, v in per_tower.items())
+    desc = (f"{len(used)} of {len(blocks)} blocks timed ({mix}; {t_total:.1f} s of CPU work on {used_threads} OpenMP threads), "
+            f"extrapolated per tower to all {len(blocks)} blocks; all Linears, {n_batches} batches of {BATCH}")
+    return tokens, est, desc
 
 
 def run_reference(args):
@@ -197,6 +213,239 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def bind_to_gpu_cpus(index):
+    """Pin this process (and therefore the first-touch placement of its pinned host buffers) to the CPU cores NVML reports
+    as local to the GPU: the e2e leg streams ~57 GB per step from host memory, and a rank scheduled on the far socket
+    pulls all of it across the inter-socket link.  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cores local to GPU {index} (NVML)"
+    except Exception as exc:  # pragma: no cover - NVML or the syscall unavailable: run unbound, say so
+        return f"unbound ({type(exc).__name__})"
+    return "unbound"
+
+
+def prune_wall(which=("wanda", "ecoflap"), verbose=False):
+    """`pruner.prune()` wall seconds -- the first item of BASELINE.json's metric -- on a full-size random-init BLIP-2
+    (EVA ViT-g fp16 + FlanT5-XL bf16, 588 Linears / 3.70 G parameters; synthetic.blip2_full) with 128 synthetic samples
+    in batches of 8, through the reference's entry point `load_pruner("blipt5_wanda_pruner", ...).prune()`:
+      wanda     uniform 50 % (reference: 240.16 s, LAVIS/training_statistics/cc3m-blipt5_wanda_pruner_0.5-1.0-1.0.yaml)
+      ecoflap   zeroth-order stage 1 (MEZO-GradOnly_sum, block granularity, max 0.6, 32 first-stage samples: 588 layers x
+                4 batches x 2 forwards) + Wanda (reference: 5 985-6 115 s, ..._olmezo-gradient_sum0.6_block_nd32.yaml)
+      sparsegpt blipt5_sparsegpt_pruner 50 %, batch size 1 as the reference asserts (reference: 802.63 s)
+    Unlike the hot-path step this INCLUDES the model forwards (two per block and batch in stage 2, two per
+    layer and batch in stage 1), i.e. mostly cuBLAS / SDPA time.  Under torchrun the calibration batches (stage 2) and the
+    layers (stage 1) are sharded over the ranks; the wall time is the max over ranks."""
+    import contextlib
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from ecoflap_b200 import ops
+    from ecoflap_b200 import synthetic as syn
+    from ecoflap_b200.compression import load_pruner
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    out = {}
+    for name in which:
+        torch.manual_seed(0)
+        np.random.seed(42)
+        model = syn.blip2_full(dev)
+        cfg = dict(t5_prune_spec="24-0.5-1.0-1.0", vit_prune_spec="39-0.5-1.0-1.0", t5_pruning_method="x",
+                   vit_pruning_method="x", num_samples=128)
+        loader = syn.blip2_full_loader(128, 8)
+        reg = "blipt5_wanda_pruner"
+        if name == "ecoflap":
+            cfg.update(sparsity_ratio_granularity="block", max_sparsity_per_layer=0.6, score_method="MEZO-GradOnly_sum",
+                       num_data_first_stage=32, num_noise=1, noise_eps=1e-3)
+        elif name == "sparsegpt":
+            reg = "blipt5_sparsegpt_pruner"
+            loader = syn.blip2_full_loader(128, 1)
+        pruner = load_pruner(reg, model, loader, cfg=cfg)
+        torch.cuda.reset_peak_memory_stats(dev)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        with open(os.devnull, "w") as sink, contextlib.redirect_stdout(sink if not verbose else sys.stderr):
+            _, sd = pruner.prune()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([wall], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wall = float(t.item())
+        zeros = total = 0
+        for k, p in model.named_parameters():
+            if p.dim() == 2 and (".blocks." in k or ".block." in k) and "relative_attention_bias" not in k:
+                zeros += int(ops.count_zero(p.data).item())
+                total += p.numel()
+        entry = {"wall_s": round(wall, 3), "sparsity": zeros / total, "linears_params": total,
+                 "peak_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 2)}
+        if isinstance(sd, dict):
+            vals = list(sd.values())
+            entry["ratio_min_max"] = [float(min(vals)), float(max(vals))]
+        out[name] = entry
+        del pruner, model
+        torch.cuda.empty_cache()
+    return out
+
+
+def aten_gpu_baseline(lins, summ_tokens, budget_s=6.0):
+    """SURVEY 8(d), last row: the reference's own ATen path ON THE SAME B200 -- what a user of ylsung/ECoFLaP runs today
+    (torch.norm hooks, |W|*sqrt(norm) materialised in fp32, torch.sort(stable) / sort(flatten), scatter_, masked store;
+    oracle/aten_reference.py restates wanda_pruner.py:54-84,260-279,541-558 call for call).  One block per tower is timed
+    with CUDA events (more while the budget lasts) and extrapolated with the workload's tower mix, like the CPU arm."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import aten_reference as aten
+
+    towers = {}
+    for pb in lins:
+        towers.setdefault((len(pb), tuple(pb[0].W.shape)), []).append(pb)
+    per_tower = {k: [0.0, 0] for k in towers}
+    spent, depth = 0.0, 0
+    while depth < max(len(t) for t in towers.values()):
+        for key, t in towers.items():
+            if depth >= len(t) or (spent >= budget_s and per_tower[key][1] > 0):
+                continue
+            pb = t[depth]
+            Ws = [o.W0.clone() for o in pb]
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for o, W in zip(pb, Ws):
+                acc = aten.AtenWrappedGPT(columns=W.shape[1], device=W.device)
+                for x in o.acts:
+                    acc.add_batch(x.view(BATCH, -1, x.shape[-1]))
+                if o.spec.select == "row":
+                    aten.prune_rows_(W, acc.scaler_row, SPARSITY)
+                else:
+                    aten.prune_layer_(W, acc.scaler_row, SPARSITY)
+            e1.record()
+            torch.cuda.synchronize()
+            sec = e0.elapsed_time(e1) * 1e-3
+            if depth > 0 or per_tower[key][1] == 0:
+                per_tower[key][0] += sec
+                per_tower[key][1] += 1
+            spent += sec
+            del Ws
+        depth += 1
+        if spent >= budget_s and all(v[1] > 0 for v in per_tower.values()):
+            break
+    torch.cuda.empty_cache()
+    est = sum(len(towers[k]) * v[0] / v[1] for k, v in per_tower.items())
+    return {"value": summ_tokens / est, "unit": "tokens/s", "ms_per_step": 1e3 * est, "kind": "restatement of the reference's ATen calls on cuda:0",
+            "sample": f"{sum(v[1] for v in per_tower.values())} of {len(lins)} blocks timed with CUDA events, extrapolated per tower"}
+
+
+def sparsegpt_roofline(dev):
+    """Tensor-pipe side of the path (north_star: Hessian and OBS kernels against the bf16 tensor peak), on the SparseGPT
+    shapes of BASELINE.json configs 2 (CLIP ViT-B/16: T = 128 x 197, C = 768 / 3072) and 4 (EVA ViT-g: T = 128 x 257,
+    C = 1408 / 6144; FlanT5-XL wo: C = 5120).  Hessian: one `ecf_hessian_accum` launch over the concatenated calibration
+    batches (what HessianBatch issues), algorithmic flops 2*T*C^2 over CUDA-event time.  OBS: `ecf_obs_prune`
+    with its phases timed separately through ECF_OBS_PHASES (tile threshold | mask + 128-step sweep | tcgen05 trailing
+    update); trailing flops R*C^2 algorithmic (the bf16 hi/mid split executes 3x that).  Prologue (A9, cuSOLVER) beside it."""
+    import torch
+
+    from ecoflap_b200 import ops
+    from ecoflap_b200.accumulators import SparseGPT
+
+    pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    peak_sus = float(pk.get("bf16_tflops_sustained", 1388.0))
+    peak_burst = float(pk.get("bf16_tflops_burst", pk.get("bf16_tflops", 1640.0)))
+    scratch = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(fn, reps=3, prepare=None):
+        fn()
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(reps):
+            if prepare is not None:
+                prepare()
+            scratch.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            t = a.elapsed_time(b)
+            best = t if best is None else min(best, t)
+        return best
+
+    out = {"peak_tflops_sustained": peak_sus, "peak_tflops_burst": peak_burst, "hessian": [], "obs": []}
+    torch.manual_seed(7)
+    for name, T, C, dt in (("cfg4 ViT-g fc2, 128 x 257 tokens", 128 * 257, 6144, torch.float16),
+                           ("cfg4 ViT-g qkv/fc1 (fp32 LayerNorm output)", 128 * 257, 1408, torch.float32),
+                           ("cfg4 T5-XL wo, 128 x 56 tokens", 128 * 56, 5120, torch.bfloat16),
+                           ("cfg2 CLIP ViT-B/16 c_proj, 128 x 197 tokens", 128 * 197, 3072, torch.float16),
+                           ("cfg2 CLIP ViT-B/16 in_proj/c_fc", 128 * 197, 768, torch.float16)):
+        X = torch.randn(T, C, device=dev).to(dt)
+        H = torch.zeros(C, C, device=dev)
+        ms = timed(lambda: ops.hessian_accum(X, H, 2.0 / 128, 0.0))
+        tf = 2.0 * T * C * C / (ms * 1e-3) / 1e12
+        # what the tensor pipe executes: only the 128 x 256 tiles that touch the upper triangle (the mirror kernel fills the
+        # rest), times three bf16 products per element for fp32 inputs (hi*hi + hi*mid + mid*hi)
+        mt, nt = -(-C // 128), -(-C // 256)
+        tiles = sum(1 for i in range(mt) for j in range(nt) if (j + 1) * 256 > i * 128)
+        ex = tf * tiles / (mt * nt) * (3.0 if dt == torch.float32 else 1.0)
+        out["hessian"].append({"shape": name, "T": T, "C": C, "dtype": str(dt).split(".")[-1], "ms": ms, "tflops_algorithmic": tf,
+                               "tflops_executed": ex, "tensor_pipe_frac_of_sustained": ex / peak_sus,
+                               "tensor_pipe_frac_of_burst": ex / peak_burst,
+                               "note": "algorithmic = 2*T*C^2 (SURVEY 8d counts the full product); executed = upper-triangle tiles only"})
+        del X, H
+    for name, R, C in (("cfg4 ViT-g fc2 1408x6144", 1408, 6144), ("cfg4 ViT-g fc1 6144x1408", 6144, 1408),
+                       ("cfg4 T5-XL wo 2048x5120", 2048, 5120), ("cfg2 CLIP c_proj 768x3072", 768, 3072),
+                       ("cfg2 CLIP c_fc 3072x768", 3072, 768)):
+        Xh = torch.randn(4 * C, C, device=dev)
+        Xh[:, 1] *= 8.0
+        H0 = (2.0 / (4 * C)) * (Xh.t() @ Xh)
+        del Xh
+        lin = torch.nn.Linear(C, R, bias=False).to(dev)
+        acc = SparseGPT(lin)
+        acc.H = H0.clone()
+        t0 = time.perf_counter()
+        torch.cuda.synchronize()
+        Hinv, _ = acc.prepare_hinv(0.01)
+        torch.cuda.synchronize()
+        prologue_ms = 1e3 * (time.perf_counter() - t0)
+        W0 = torch.randn(R, C, device=dev) * 0.02
+        W = W0.clone()
+        kth = [int(R * (min(i1 + 128, C) - i1) * 0.5) for i1 in range(0, C, 128)]
+        ph = {}
+        for tag, mask in (("all", 7), ("threshold", 1), ("threshold+sweep", 3)):
+            os.environ["ECF_OBS_PHASES"] = str(mask)
+            ph[tag] = timed(lambda: ops.obs_prune(W, Hinv, kth), prepare=lambda: W.copy_(W0))
+        os.environ.pop("ECF_OBS_PHASES", None)
+        trailing = max(ph["all"] - ph["threshold+sweep"], 1e-6)
+        tf = float(R) * C * C / (trailing * 1e-3) / 1e12
+        out["obs"].append({"shape": name, "R": R, "C": C, "total_ms": ph["all"], "threshold_ms": ph["threshold"],
+                           "sweep_ms": ph["threshold+sweep"] - ph["threshold"], "trailing_ms": trailing,
+                           "trailing_tflops_algorithmic": tf, "trailing_frac_of_sustained": tf / peak_sus,
+                           "trailing_tflops_executed_x3_split": 3 * tf, "prologue_cusolver_ms": prologue_ms})
+        del H0, Hinv, W, W0, acc, lin
+    del scratch
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -213,6 +462,8 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cpus = os.sched_getaffinity(0)
+    affinity = bind_to_gpu_cpus(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     TD = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
@@ -269,8 +520,9 @@ def run_b200(args):
             print(f"[bench] peer-memory exchange unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
             pex = None
 
-    def step_device():
-        """one pass, everything resident in HBM.  Per block: the hook calls of its 16 calibration batches are
+    def step_device(batches=range(N_BATCHES)):
+        """one pass, everything resident in HBM (``batches``: the calibration batches this rank accumulates -- all 16 of its
+        own shard under weak scaling, every world-th of the one fixed set under strong scaling).  Per block: the hook calls of its 16 calibration batches are
         deferred into batched norm launches (<= 256 hook calls / 32 accumulators each), then the fused select of
         every Linear; the selects of a block are independent, so each runs on its own stream and they overlap under
         CUDA-graph replay."""
@@ -279,7 +531,7 @@ def run_b200(args):
             nb = NormBatch()
             accs = [WrappedGPT(o.layer, batch=nb) for o in pb]
             flat = edist.pack_block_norms(accs) if world > 1 else None  # one buffer per block: one in-place all-reduce
-            for j in range(N_BATCHES):
+            for j in batches:
                 for o, acc in zip(pb, accs):
                     acc.add_batch(o.acts[j])
             nb.flush()
@@ -373,6 +625,38 @@ def run_b200(args):
     tokens_per_step = summ["calib_tokens_per_step"] * world
     value = tokens_per_step / (step_ms * 1e-3)
 
+    # ---- strong scaling (N > 1): BASELINE.json configs[3] as written -- the ONE 128-sample calibration set sharded over the
+    # ranks (rank r accumulates batches r, r + N, ...), exchange, every rank selects.  Reported next to the weak-scaling
+    # headline; the replicated select is what bounds it (Amdahl).
+    strong = None
+    if world > 1:
+        mine = range(rank, N_BATCHES, world)
+        restore()
+        step_device(mine)
+        torch.cuda.synchronize()
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2):
+            step_device(mine)
+        st = []
+        for i in range(3 + args.steps):
+            restore()
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g2.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                st.append(e0.elapsed_time(e1))
+        t = torch.tensor([sum(st) / len(st)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        strong_ms = float(t.item())
+        strong = {"ms_per_step": strong_ms, "value": summ["calib_tokens_per_step"] / (strong_ms * 1e-3), "unit": "tokens/s",
+                  "samples": N_BATCHES * BATCH, "batches_per_rank": len(mine),
+                  "limiter": "replicated per-row / per-layer select (every rank prunes every Linear) + one exchange per block"}
+        del g2
+
     # ---- roofline of the kernel families ------------------------------------------------------------------------
     # The sampled launches of a family (every sixth block of every tower) are captured back to back in ONE CUDA graph and
     # replayed between two events on the launching stream: device time only, and the ~8 us between an event record and the
@@ -410,6 +694,7 @@ def run_b200(args):
         return best
 
     sq_fns, lt_fns, rs_fns, lt_lins, rs_lins = [], [], [], [], []
+    sq_distinct = 0
     sampled = lins[::6]  # every sixth block: 7 ViT-g, 4 T5 encoder, 4 T5 decoder blocks, ~100 Linears
     # blocks of one tower share their (synthetic) activation tensors: interleave the towers so that two launches reading the
     # same tensors are > 1 GB of other traffic apart
@@ -426,6 +711,11 @@ def run_b200(args):
                 items.append((o.acts[j], acc.scaler_row, n0 / (n0 + BATCH), 1.0 / (n0 + BATCH)))
         sq_fns.append(lambda items=items: ops.sqnorm_accum_batched(items))
         fam["sqnorm"][1] += sum(wl.norm_bytes(o.spec, N_BATCHES) for o in pb)
+        seen_x = {}
+        for o in pb:  # distinct input bytes: hooks that see the very same tensor (q/k/v ...) are read once by the kernel
+            for x in o.acts:
+                seen_x[x.data_ptr()] = x.numel() * x.element_size()
+        sq_distinct += sum(seen_x.values()) + sum(8 * o.spec.cols for o in pb)
         fam["sqnorm"][2] += -(-len(items) // _abi.SQNORM_MAX_BATCH)
         layer = [(o, acc) for o, acc in zip(pb, accs) if o.spec.select == "layer"]
         if layer:
@@ -452,6 +742,11 @@ def run_b200(args):
         if n:
             kernels[name] = {"launches": n, "avg_us": 1e3 * ms / n, "achieved_gbs": nbytes / ms / 1e6,
                              "frac": nbytes / ms / 1e6 / peak, "time_share": ms}
+    if "sqnorm" in kernels:
+        # frac counts every hook's input (T*C*sizeof(x) + 8*C per hook call); shared inputs are read once, so the
+        # bytes the kernel actually has to move are fewer: both fractions are reported
+        kernels["sqnorm"]["achieved_gbs_distinct_bytes"] = sq_distinct / fam["sqnorm"][0] / 1e6
+        kernels["sqnorm"]["frac_distinct_bytes"] = sq_distinct / fam["sqnorm"][0] / 1e6 / peak
     tot_ms = sum(v["time_share"] for v in kernels.values())
     for v in kernels.values():
         v["time_share"] = v["time_share"] / tot_ms
@@ -467,9 +762,15 @@ def run_b200(args):
             traffic_of = {"launch": tr["launch"], "algorithmic_bytes_per_launch": tr["algorithmic_bytes_per_launch"], "source": tr["source"]}
     except (OSError, ValueError, KeyError):
         pass
-    roofline = {"bound": "hbm", "kernel": dominant, "achieved": kernels[dominant]["achieved_gbs"], "peak": peak,
-                "unit": "GB/s", "frac": kernels[dominant]["frac"], "traffic": traffic, "traffic_of": traffic_of,
-                "peak_source": peak_src, "kernels": kernels}
+    # headline of the dominant kernel: for the norms the bytes the kernel has to move (shared hook inputs once); the per-hook
+    # figure of SURVEY 8(d) is next to it and can exceed 1 because it counts a shared input once per hook
+    head = kernels[dominant]
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": head.get("achieved_gbs_distinct_bytes", head["achieved_gbs"]),
+                "peak": peak, "unit": "GB/s", "frac": head.get("frac_distinct_bytes", head["frac"]),
+                "frac_per_hook_bytes": head["frac"], "traffic": traffic, "traffic_of": traffic_of,
+                "peak_source": peak_src + "; the peak is a COPY (read + write) bandwidth, a read-only stream can exceed it",
+                "method": "one CUDA graph per kernel family over the sampled launches, CUDA events around the replay, clean L2 flush",
+                "kernels": kernels}
 
     # ---- e2e: host buffers through the public API ------------------------------------------------------------
     e2e = None
@@ -508,7 +809,7 @@ def run_b200(args):
                     seen.add(l.src or l.name)
                     h2d += l.tokens * l.cols * wl.BYTES[l.x_dtype] * N_BATCHES
 
-        def step_e2e():
+        def step_e2e(batches=range(N_BATCHES)):
             slot_i = 0
             for e in ev_free:
                 e.record(s_comp)
@@ -529,7 +830,7 @@ def run_b200(args):
                     for o in members:
                         accs.append(WrappedGPT(o.layer))
                     src = host_act[ka]
-                    for j in range(N_BATCHES):
+                    for j in batches:
                         k = slot_i % RING
                         slot_i += 1
                         stage = ring[k][:src.numel() * src.element_size()].view(src.dtype).view(src.shape)
@@ -541,6 +842,8 @@ def run_b200(args):
                         for acc in accs:
                             acc.add_batch(stage)  # per-hook launch on the compute stream
                         ev_free[k].record(s_comp)
+                    if world > 1:  # the exchange step: global running means over the batches of all ranks
+                        edist.sync_block_norms(accs)
                     s_comp.wait_event(w_ready)
                     done = torch.cuda.Event()
                     for o, acc in zip(members, accs):
@@ -570,10 +873,51 @@ def run_b200(args):
             e2e_s = float(t.item())
         e2e = {"value": tokens_per_step / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s, "steps": n_e2e}
+        if world > 1:  # strong scaling through the public API: this rank copies in only its share of the batches
+            mine = range(rank, N_BATCHES, world)
+            step_e2e(mine)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                step_e2e(mine)
+            barrier()
+            t = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            strong["e2e_value"] = summ["calib_tokens_per_step"] / float(t.item())
+            strong["e2e_ms_per_step"] = 1e3 * float(t.item())
+
+    # ---- the reference's ATen path on this GPU, the tensor-core kernels, prune() wall seconds ------------------------
+    aten = None
+    if rank == 0 and world == 1 and not args.no_aten:
+        aten = aten_gpu_baseline(lins, summ["calib_tokens_per_step"])
+    # free the resident hot-path data before the full-size model runs
+    graph = None
+    run_step = None
+    for o in flat:
+        o.W = o.W0 = o.acts = o.layer = None
+    lins, flat, act_pool = [], [], {}
+    import gc
+
+    gc.collect()
+    torch.cuda.empty_cache()
+    sgpt = None
+    if rank == 0 and not args.no_sparsegpt_kernels:
+        sgpt = sparsegpt_roofline(dev)
+        roofline["tensor"] = sgpt
+    walls = None
+    which = [w for w in args.prune_wall.split(",") if w and w != "none"]
+    if which:
+        walls = prune_wall(which)
+        ref_s = {"wanda": 240.16, "ecoflap": 5985.24, "sparsegpt": 802.63}
+        for k, v in walls.items():
+            v["reference_wall_s"] = ref_s.get(k)
+            v["reference_hardware"] = "one GPU, model unstated (LAVIS/training_statistics/*.yaml; BASELINE.md section 1)"
+            v["n_gpus"] = world
 
     # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        os.sched_setaffinity(0, all_cpus)  # the CPU arm gets every host core back
         threads = os.cpu_count() or 1
         tok, sec, desc = cpu_reference_pass(blocks, N_BATCHES, args.cpu_sample_s, threads)
         cpu = {"value": tok / sec, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": desc, "seconds": sec}
@@ -593,8 +937,9 @@ def run_b200(args):
                        "timing": "CUDA events per step, max over ranks; weights restored between steps outside the events",
                        "bracket_ms": bracket_ms, "launch": launch_mode, "parallelism": f"dp{world}: batch-sharded norms + " + ("peer-memory exchange kernel (NVSwitch P2P)" if pex is not None else "NCCL all-reduce") + " per block; select " + ("row-sharded + all-gather" if ROW_SHARD and world > 1 else "replicated per rank")},
             "prune_wall_s_hot_path": step_ms * 1e-3,
+            "prune_wall_s": walls, "aten_gpu_baseline": aten, "strong_scaling": strong,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "clocks": clocks, "abi_version": _abi.lib.ecf_version(),
+            "clocks": clocks, "abi_version": _abi.lib.ecf_version(), "cpu_affinity": affinity,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

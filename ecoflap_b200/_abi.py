@@ -13,7 +13,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libecoflap_b200.so")
 
 ECF_F32, ECF_F16, ECF_BF16 = 0, 1, 2
-OP_SQNORM, OP_ROW_SELECT, OP_LAYER_THRESH, OP_GROUP_REDUCE, OP_HESSIAN, OP_OBS = range(6)
+OP_SQNORM, OP_ROW_SELECT, OP_LAYER_THRESH, OP_GROUP_REDUCE, OP_HESSIAN, OP_OBS, OP_GLOBAL_SELECT = range(7)
+GLOBAL_MAG, GLOBAL_GRAD_MAG_ABS, GLOBAL_GRAD_MAG_SQ, GLOBAL_GRAD_ONLY = range(4)
 ERR_INVALID, ERR_WORKSPACE, ERR_CUDA, ERR_NO_DEVICE, ERR_RANGE = -1, -2, -3, -4, -5
 
 EXPORTED = (
@@ -23,6 +24,7 @@ EXPORTED = (
     "ecf_layer_thresh_batched_workspace_bytes", "ecf_layer_thresh_flag_offset", "ecf_wanda_layer_thresh_apply_batched", "ecf_group_reduce_chunk_elems",
     "ecf_norm_exchange_staging_bytes", "ecf_norm_exchange_p2p",
     "ecf_group_abs_reduce", "ecf_zo_perturb", "ecf_count_zero", "ecf_hessian_accum", "ecf_obs_prune",
+    "ecf_global_chunk_elems", "ecf_global_select", "ecf_global_apply",
 )
 
 
@@ -34,6 +36,11 @@ class EcfError(RuntimeError):
 
 class TensorDesc(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("numel", C.c_int64), ("dtype", C.c_int32), ("reserved", C.c_int32),
+                ("chunk_begin", C.c_int64)]
+
+
+class GlobalDesc(C.Structure):
+    _fields_ = [("W", C.c_void_p), ("G", C.c_void_p), ("numel", C.c_int64), ("dtype", C.c_int32), ("reserved", C.c_int32),
                 ("chunk_begin", C.c_int64)]
 
 
@@ -91,6 +98,9 @@ def _load():
         "ecf_count_zero": (i32, [vp, i32, i64, vp, vp]),
         "ecf_hessian_accum": (i32, [vp, i32, i64, i64, i64, vp, i64, f32, f32, vp, sz, vp]),
         "ecf_obs_prune": (i32, [vp, i64, i64, i64, vp, i64, C.POINTER(C.c_int64), i32, vp, sz, vp]),
+        "ecf_global_chunk_elems": (i64, []),
+        "ecf_global_select": (i32, [vp, i32, i64, i32, f64, i32, vp, vp, vp, vp, sz, vp]),
+        "ecf_global_apply": (i32, [vp, i32, i64, i32, f64, i32, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -369,6 +369,10 @@ extern "C" int ecf_obs_prune(float* W, int64_t R, int64_t C, int64_t ldw, const 
   }
   ECF_CUDA_OK(cudaMemsetAsync(o.hist, 0, 2048 * sizeof(unsigned), stream));
 
+  // ECF_OBS_PHASES (profiling aid, read per call): bit 0 tile threshold, bit 1 mask + 128-step sweep, bit 2 trailing update.
+  // Anything but 7 leaves W incomplete; bench.py uses it to time the phases separately.
+  const char* ph_env = getenv("ECF_OBS_PHASES");
+  const int phases = ph_env != nullptr ? atoi(ph_env) : 7;
   for (int b = 0; b < nblocks; ++b) {
     const int i1 = b * kObsBlock;
     const int i2 = (int)(i1 + kObsBlock < C ? i1 + kObsBlock : C);
@@ -377,20 +381,24 @@ extern "C" int ecf_obs_prune(float* W, int64_t R, int64_t C, int64_t ldw, const 
     int64_t g = (elems + 255) / 256;
     if (g > (int64_t)sms * 8) g = (int64_t)sms * 8;
     const unsigned grid = (unsigned)g;
-    obs_hist_kernel<0><<<grid, 256, 0, stream>>>(W, R, ldw, Hinv, ldh, i1, count, o.state, o.hist);
-    lt_scan_kernel<11, true><<<1, 1024, 0, stream>>>(o.state, o.hist, (unsigned long long)kth_per_block[b]);
-    obs_hist_kernel<1><<<grid, 256, 0, stream>>>(W, R, ldw, Hinv, ldh, i1, count, o.state, o.hist);
-    lt_scan_kernel<10, false><<<1, 1024, 0, stream>>>(o.state, o.hist, 0ull);
-    obs_hist_kernel<2><<<grid, 256, 0, stream>>>(W, R, ldw, Hinv, ldh, i1, count, o.state, o.hist);
-    lt_scan_kernel<10, false><<<1, 1024, 0, stream>>>(o.state, o.hist, 0ull);
-    int64_t gm = (R * 4 + 7) / 8;
-    if (gm > (int64_t)sms * 8) gm = (int64_t)sms * 8;
-    obs_mask_kernel<<<(unsigned)gm, 256, 0, stream>>>(W, R, ldw, Hinv, ldh, i1, count, o.state, o.mask);
-    int64_t gs = (R + 7) / 8;
-    if (gs > (int64_t)sms * 3) gs = (int64_t)sms * 3;
-    obs_sweep_kernel<<<(unsigned)gs, 256, kObsBlock * kObsBlock * 4, stream>>>(W, R, ldw, Hinv, ldh, i1, count, o.mask, o.err_hi,
-                                                                              o.err_mid);
-    if (i2 < C) {
+    if (phases & 1) {
+      obs_hist_kernel<0><<<grid, 256, 0, stream>>>(W, R, ldw, Hinv, ldh, i1, count, o.state, o.hist);
+      lt_scan_kernel<11, true><<<1, 1024, 0, stream>>>(o.state, o.hist, (unsigned long long)kth_per_block[b]);
+      obs_hist_kernel<1><<<grid, 256, 0, stream>>>(W, R, ldw, Hinv, ldh, i1, count, o.state, o.hist);
+      lt_scan_kernel<10, false><<<1, 1024, 0, stream>>>(o.state, o.hist, 0ull);
+      obs_hist_kernel<2><<<grid, 256, 0, stream>>>(W, R, ldw, Hinv, ldh, i1, count, o.state, o.hist);
+      lt_scan_kernel<10, false><<<1, 1024, 0, stream>>>(o.state, o.hist, 0ull);
+    }
+    if (phases & 2) {
+      int64_t gm = (R * 4 + 7) / 8;
+      if (gm > (int64_t)sms * 8) gm = (int64_t)sms * 8;
+      obs_mask_kernel<<<(unsigned)gm, 256, 0, stream>>>(W, R, ldw, Hinv, ldh, i1, count, o.state, o.mask);
+      int64_t gs = (R + 7) / 8;
+      if (gs > (int64_t)sms * 3) gs = (int64_t)sms * 3;
+      obs_sweep_kernel<<<(unsigned)gs, 256, kObsBlock * kObsBlock * 4, stream>>>(W, R, ldw, Hinv, ldh, i1, count, o.mask, o.err_hi,
+                                                                                o.err_mid);
+    }
+    if (i2 < C && (phases & 4)) {
       TrailParams p;
       p.W = W; p.ldw = ldw; p.R = (int)R; p.i1 = i1; p.i2 = i2; p.C = (int)C;
       p.MT = (int)((R + kTBM - 1) / kTBM);

@@ -183,9 +183,16 @@ class PeerNormExchange:
 
 def sync_block_hessians(accumulators, group=None):
     accs = list(accumulators)
-    totals = allreduce_running_means([a.H for a in accs], [a.nsamples for a in accs], group)
-    for a, n in zip(accs, totals):
-        a.nsamples = n
+    # accumulators fed by identical inputs share one H tensor (HessianBatch): reduce every distinct matrix once
+    uniq, owner = [], {}
+    for a in accs:
+        key = a.H.data_ptr()
+        if key not in owner:
+            owner[key] = len(uniq)
+            uniq.append(a)
+    totals = allreduce_running_means([a.H for a in uniq], [a.nsamples for a in uniq], group)
+    for a in accs:
+        a.nsamples = totals[owner[a.H.data_ptr()]]
 
 
 def row_sharded_select(W: torch.Tensor, select_rows: Callable[[torch.Tensor], None], group=None):

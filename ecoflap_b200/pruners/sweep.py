@@ -23,7 +23,7 @@ import torch.nn as nn
 
 from .. import dist as edist
 from .. import ops
-from ..accumulators import NormBatch, SparseGPT, WrappedGPT
+from ..accumulators import HessianBatch, NormBatch, SparseGPT, WrappedGPT
 
 
 def get_module_recursive(base, module_to_process):
@@ -177,10 +177,12 @@ def sweep_blocks(pruner, model, dataloader, device, spec: SweepSpec, model_prefi
         subset = find_layers(layer)
         # Wanda: the hook calls of the block's calibration sweep are deferred and become one batched norm launch
         norm_batch = NormBatch() if (method == "wanda" and os.environ.get("ECF_NORM_BATCH", "1") != "0") else None
+        # SparseGPT: likewise -- one tensor-core launch per distinct hook input over the concatenated batches
+        hess_batch = HessianBatch() if (method != "wanda" and os.environ.get("ECF_HESSIAN_BATCH", "1") != "0") else None
         if method == "wanda":
             wrapped = {name: WrappedGPT(subset[name], batch=norm_batch) for name in subset}
         else:
-            wrapped = {name: acc_cls(subset[name]) for name in subset}
+            wrapped = {name: acc_cls(subset[name], batch=hess_batch) for name in subset}
 
         def make_hook(name):
             permute = restore is not None and not name.startswith("hacky")
@@ -203,6 +205,8 @@ def sweep_blocks(pruner, model, dataloader, device, spec: SweepSpec, model_prefi
                         outs[j] = _run_block(layer, inps[j], caches[j], spec)
             if norm_batch is not None:  # one launch for the whole calibration sweep of this block
                 norm_batch.flush()
+            if hess_batch is not None:
+                hess_batch.flush()
             if world > 1:  # global running means over the batches of all ranks (one all-reduce for the block)
                 if method == "wanda":
                     edist.sync_block_norms(list(wrapped.values()))

@@ -672,3 +672,42 @@ def init_weights_(model, std=0.02, seed=0):
                 m.weight.copy_(1.0 + 0.3 * torch.randn(m.weight.shape, generator=g))
                 m.bias.copy_(0.3 * torch.randn(m.bias.shape, generator=g))
     return model
+
+
+# =====================================================================================  full-size BLIP-2 (bench)
+BLIP2_VIT_G = dict(img_size=224, patch=14, dim=1408, depth=39, heads=16, mlp_hidden=6144)        # eva_vit.py:444-470
+FLAN_T5_XL = dict(vocab=32128, d_model=2048, heads=32, d_kv=64, d_ff=5120, depth=24)             # google/flan-t5-xl config
+
+
+def blip2_full(device, seed=0):
+    """Random-init BLIP-2 at the real size (EVA ViT-g fp16 + FlanT5-XL bf16: 588 prunable Linears, 3.70 G parameters),
+    built and initialised on the device (N(0, 0.02^2) matrices, randomised LayerNorm affines as in init_weights_)."""
+    with torch.device(device):
+        model = Blip2Model(vit_kw=BLIP2_VIT_G, t5_kw=FLAN_T5_XL, n_query=32, autocast=True)
+    g = torch.Generator(device=device).manual_seed(seed)
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() >= 2:
+                p.normal_(0.0, 0.02, generator=g)
+        for m in model.modules():
+            if isinstance(m, nn.LayerNorm) and m.elementwise_affine:
+                m.weight.copy_(1.0 + 0.3 * torch.randn(m.weight.shape, generator=g, device=device))
+                m.bias.copy_(0.3 * torch.randn(m.bias.shape, generator=g, device=device))
+    model.visual_encoder.half()
+    model.ln_vision.half()
+    model.t5_model.bfloat16()
+    model.t5_proj.bfloat16()
+    return model.eval()
+
+
+def blip2_full_loader(n=128, batch=8, text_len=24, tgt_len=32, seed=0):
+    """128 synthetic (image, prompt, target) samples in batches of 8: 32 query + 24 prompt tokens
+    into the T5 encoder, 32 target tokens into the decoder."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n // batch):
+        out.append({"image": torch.randn(batch, 3, 224, 224, generator=g).half(),
+                    "input_ids": torch.randint(1, 32128, (batch, text_len), generator=g),
+                    "labels": torch.randint(1, 32128, (batch, tgt_len), generator=g),
+                    "text_input": ["synthetic"] * batch})
+    return ListLoader(out)

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ECF_ABI_VERSION 3 /* 2: batched per-row select, n:m select, peer-memory norm exchange; 3: cutoff-path per-layer select, flag offset */
+#define ECF_ABI_VERSION 4 /* 2: batched per-row select, n:m select, peer-memory norm exchange; 3: cutoff-path per-layer select, flag offset; 4: global select / apply */
 
 #if defined(__GNUC__)
 #define ECF_API __attribute__((visibility("default")))
@@ -59,7 +59,8 @@ enum ecf_op {
   ECF_OP_LAYER_THRESH = 2,
   ECF_OP_GROUP_REDUCE = 3,
   ECF_OP_HESSIAN = 4,
-  ECF_OP_OBS = 5
+  ECF_OP_OBS = 5,
+  ECF_OP_GLOBAL_SELECT = 6 /* R = number of segments (1 = one global threshold, n = one per tensor), C unused */
 };
 
 ECF_API int ecf_version(void);
@@ -205,6 +206,34 @@ ECF_API int64_t ecf_group_reduce_chunk_elems(void);
 ECF_API int ecf_group_abs_reduce(const ecf_tensor_desc* d_table, int n_tensors, int64_t total_chunks,
                          double* sum_abs, double* sum_sq,
                          void* ws, size_t ws_bytes, ecf_stream_t stream);
+
+/* N3 -- global-pruner baselines: BLIPT5GlobalPruner.get_mask / get_layerwise_mask, global_pruner.py:116-157, and
+ * LayerSparsity.get_mask of the 'Real*' ratio oracle, layer_single_base_pruner.py:156-181.
+ *   thr = topk(cat(flatten(score_t)), int(p * numel), largest=False)[-1];   w_t *= (score_t > thr)
+ * The scores are recomputed from W (and the accumulated |grad| / grad^2 sums G, n_batches) inside a 3-digit radix select
+ * over a DEVICE table of tensors; nothing is materialised.  `segmented` != 0: one select / threshold per tensor
+ * (get_layerwise_mask; the per-tensor protection thresholds of get_mask).  d_ranks[seg]: 0-based ascending rank of the
+ * wanted score (host: int(p * numel) - 1; numel_t - int(numel_t * (1 - max_sparsity)) for a protection threshold).
+ * d_protect (nullable): per-tensor key at or above which a score counts as finfo.max (output of a previous segmented
+ * select).  d_tkeys [segments]: order-preserving uint32 key of the threshold (ecf_global_select writes, _apply reads).
+ * Pruned weights keep their sign bit (w * 0.0), like `v.data *= mask`.  chunk_begin as in ecf_tensor_desc, with
+ * ecf_global_chunk_elems()-sized chunks. */
+enum { ECF_GLOBAL_MAG = 0, ECF_GLOBAL_GRAD_MAG_ABS = 1, ECF_GLOBAL_GRAD_MAG_SQ = 2, ECF_GLOBAL_GRAD_ONLY = 3 };
+typedef struct ecf_global_desc {
+  void* W;
+  const float* G; /* fp32 [numel] sum over the batches of |grad| (grad^2 for GRAD_MAG_SQ); unused for ECF_GLOBAL_MAG */
+  int64_t numel;
+  int32_t dtype;
+  int32_t reserved;
+  int64_t chunk_begin;
+} ecf_global_desc;
+ECF_API int64_t ecf_global_chunk_elems(void);
+ECF_API int ecf_global_select(const ecf_global_desc* d_table, int n_tensors, int64_t total_chunks, int mode, double n_batches,
+                      int segmented, const uint32_t* d_protect, const long long* d_ranks, uint32_t* d_tkeys,
+                      void* ws, size_t ws_bytes, ecf_stream_t stream);
+ECF_API int ecf_global_apply(const ecf_global_desc* d_table, int n_tensors, int64_t total_chunks, int mode, double n_batches,
+                     int segmented, const uint32_t* d_protect, const uint32_t* d_tkeys, unsigned long long* d_n_pruned,
+                     ecf_stream_t stream);
 
 /* A11 -- LayerSparsity.zo_perturb_parameters, layer_single_base_pruner.py:473-486.
  *   w = rn(w + rn(rn(scaling * z) * eps)), each rounding in the parameter dtype (torch evaluates

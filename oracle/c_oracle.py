@@ -36,7 +36,16 @@ def lib():
         _lib.ecf_ref_wanda_row_prune.restype = None
         _lib.ecf_ref_wanda_layer_prune.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]
         _lib.ecf_ref_wanda_layer_prune.restype = C.c_float
+        _lib.ecf_ref_set_threads.argtypes = [C.c_int]
+        _lib.ecf_ref_set_threads.restype = None
+        _lib.ecf_ref_max_threads.restype = C.c_int
     return _lib
+
+
+def set_threads(n):
+    """OpenMP threads of the C oracle, set explicitly (an inherited OMP_NUM_THREADS=1 would silently serialise it)."""
+    lib().ecf_ref_set_threads(int(n))
+    return int(lib().ecf_ref_max_threads())
 
 
 def to_storage(a_f32, dtype):

@@ -10,6 +10,7 @@
  * Parity: pinned against tests/golden (generated from the reference) through tests/test_oracle_c.py.
  */
 #include <math.h>
+#include <omp.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -127,3 +128,9 @@ float ecf_ref_wanda_layer_prune(void* W, int dtype, int64_t R, int64_t C, const 
   free(sorted);
   return thres;
 }
+
+
+/* host threads used by the OpenMP loops above (torchrun exports OMP_NUM_THREADS=1 to its workers: the benchmark's
+ * reference arm sets the count explicitly) */
+void ecf_ref_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int ecf_ref_max_threads(void) { return omp_get_max_threads(); }

@@ -806,3 +806,47 @@ def test_prepare_hinv_reference_golden_end_to_end():
         got, ref = f32(lin.weight.data), g[f"{name}__Wout"]
         assert ((got == 0) == (ref == 0)).mean() >= 0.995, name
         assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 2e-2, name
+
+
+def test_hessian_batch_matches_per_call_updates_and_shares_identical_inputs():
+    """HessianBatch: one launch over the concatenated batches == the reference's per-batch running update
+    (sparsegpt_pruner.py:71-82) to fp32 summation order; Linears fed the very same tensors (q/k/v) get ONE Hessian and
+    ONE inverse-Cholesky factor; fasterprune through the shared factor equals fasterprune through a private one."""
+    from ecoflap_b200.accumulators import HessianBatch, SparseGPT
+
+    torch.manual_seed(3)
+    C, R = 256, 96
+    lins = [torch.nn.Linear(C, R, bias=False).to(dev()).half() for _ in range(4)]  # q, k, v share inputs; o has its own
+    xs_shared = [(torch.randn(1, 37 + 5 * j, C, device=dev()) * (1 + 0.1 * j)).half() for j in range(6)]
+    xs_own = [(torch.randn(1, 41, C, device=dev())).half() for j in range(6)]
+    hb = HessianBatch()
+    batched = [SparseGPT(l, batch=hb) for l in lins]
+    plain = [SparseGPT(l) for l in lins]
+    ref = orc.HessianAccumulator(C)
+    for j in range(6):
+        for i in range(4):
+            x = xs_shared[j] if i < 3 else xs_own[j]
+            batched[i].add_batch(x)
+            plain[i].add_batch(x)
+        ref.add_batch(f32(xs_shared[j]))
+    assert len(hb) == 24 and batched[0].nsamples == 0
+    hb.flush()
+    assert all(a.nsamples == 6 for a in batched)
+    assert batched[0].H.data_ptr() == batched[1].H.data_ptr() == batched[2].H.data_ptr() != batched[3].H.data_ptr()
+    for i in range(4):
+        scale = float(plain[i].H.abs().max())
+        assert float((batched[i].H - plain[i].H).abs().max()) <= 2e-5 * scale, i
+    assert np.abs(f32(batched[0].H) - ref.H).max() <= 1e-4 * np.abs(ref.H).max()
+    W0 = [l.weight.data.clone() for l in lins]
+    for a in batched:
+        a.fasterprune(0.5)
+    got = [l.weight.data.clone() for l in lins]
+    assert batched[1]._hinv_share is batched[0]._hinv_share and "hinv" in batched[0]._hinv_share
+    for l, w in zip(lins, W0):
+        l.weight.data = w.clone()
+    for a in plain:
+        a.fasterprune(0.5)
+    for i, l in enumerate(lins):
+        a, b = f32(got[i]), f32(l.weight.data)
+        assert ((a == 0) == (b == 0)).mean() >= 0.999, i
+        assert np.linalg.norm(a - b) / np.linalg.norm(b) < 2e-3, i
