@@ -108,9 +108,8 @@ class LayerSparsity:
     def return_sparsity(self):
         mapping = self.layer_to_group_mapping
         if self.score_compute.startswith("Real"):
-            raise NotImplementedError(
-                "'Real*' score methods run the 3-iteration global pruning baseline as a ratio oracle "
-                "(layer_single_base_pruner.py:321-325); that baseline is outside the hot path (SURVEY section 8 f, N3)")
+            # the 3-iteration global pruning run as a ratio oracle (layer_single_base_pruner.py:321-325)
+            return self.global_iterative_pruning(self.original_sparsity, mapping, iteratation=3, max_sparsity_per_layer=1.0)
         if mapping is None or len(mapping) == 0:
             return _UniformSparsity(self.original_sparsity)
 
@@ -154,6 +153,41 @@ class LayerSparsity:
         kept = sum((1 - group_sparsity[g]) * group_sizes[g] for g in group_sizes)
         print(kept, total_to_keep)  # the reference's sanity line (:407)
         return {layer: group_sparsity[group] for layer, group in mapping.items()}
+
+    # ------------------------------------------------------------------ 'Real*' ratio oracle (N3 machinery)
+    def global_iterative_pruning(self, target_sparsity, dict_layers_to_prune, iteratation=1, max_sparsity_per_layer=1.0):
+        """layer_single_base_pruner.py:183-245: prune globally by the first-order score in ``iteratation`` rounds
+        (p_i = target ** (iteratation / i)), read every parameter's zero fraction, restore the weights.  The per-element
+        scores are never built: the gradient sums stay on the device and the select recomputes |w| * |g| on the fly
+        (pruners/global_pruner.py, csrc/global_select.cu).  Reference detail kept: the gradient accumulation squares only
+        when score_compute == "GradMagSquare" EXACTLY (:447), which a 'Real*' name never is, so 'RealGradMagSquare' scores
+        w^2 * mean|g|."""
+        from .pruners.global_pruner import accumulate_abs_grads, device_get_mask_
+
+        names, params = self._selected(dict_layers_to_prune)
+        weight_copy = [p.data.clone() for p in params]
+        if "GradMagSquare" in self.score_compute:
+            mode = "grad_mag_sq"
+        elif "GradMagAbs" in self.score_compute:
+            mode = "grad_mag_abs"
+        elif "GradOnly" in self.score_compute:
+            mode = "grad_only"
+        else:
+            raise ValueError(f"unknown first-order score method {self.score_compute!r}")
+        for i in range(1, iteratation + 1):
+            p_i = target_sparsity ** (iteratation / i)
+            G, nb = accumulate_abs_grads(self.model, self.data_loader, self.loss_func, names, params, self.num_samples,
+                                         square=(self.score_compute == "GradMagSquare"))
+            device_get_mask_(params, G, nb, mode, p_i, max_sparsity_per_layer)
+            del G
+            print(f"Step {i}, target sparsity: {p_i:.4f}")
+        sparsity_dict = {}
+        for k, v in self.model.named_parameters():
+            z = int(ops.count_zero(v.data if v.data.is_contiguous() else v.data.contiguous()).item())
+            sparsity_dict[k] = (torch.tensor(float(z), dtype=torch.float32) / v.numel()).item()
+        for p, w in zip(params, weight_copy):
+            p.data = w
+        return sparsity_dict
 
     # ------------------------------------------------------------------ helpers
     def _selected(self, mapping):

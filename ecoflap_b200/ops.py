@@ -285,6 +285,74 @@ def group_abs_reduce(tensors):
     return sum_abs, sum_sq
 
 
+GLOBAL_MODES = {"mag": _abi.GLOBAL_MAG, "grad_mag_abs": _abi.GLOBAL_GRAD_MAG_ABS, "grad_mag_sq": _abi.GLOBAL_GRAD_MAG_SQ,
+                "grad_only": _abi.GLOBAL_GRAD_ONLY}
+
+
+class GlobalTable:
+    """Device table of the tensors a global-pruner step works on (N3; global_pruner.py:116-207).  ``weights``: contiguous
+    parameter tensors pruned in place; ``grads``: matching fp32 sums of |grad| (grad^2) over ``n_batches`` batches, or None
+    for the magnitude score."""
+
+    def __init__(self, weights, grads=None, n_batches=1, mode="mag"):
+        _require_cuda(*weights)
+        assert all(w.is_contiguous() for w in weights), "global select: parameters must be contiguous"
+        self.weights, self.grads = list(weights), grads
+        self.mode, self.n_batches = GLOBAL_MODES[mode], float(n_batches)
+        self.dev = weights[0].device
+        chunk = lib.ecf_global_chunk_elems()
+        n = len(weights)
+        table = (_abi.GlobalDesc * n)()
+        cb = 0
+        for i, w in enumerate(weights):
+            g = None if grads is None else grads[i]
+            if g is not None:
+                assert g.dtype == torch.float32 and g.is_contiguous() and g.numel() == w.numel() and g.device == w.device
+            else:
+                assert self.mode == _abi.GLOBAL_MAG, "this score mode needs the accumulated gradients"
+            assert w.numel() < (1 << 32), "global select: tensors beyond 2^32 elements are not supported"
+            table[i].W = w.data_ptr()
+            table[i].G = 0 if g is None else g.data_ptr()
+            table[i].numel = w.numel()
+            table[i].dtype = dtype_code(w)
+            table[i].reserved = 0
+            table[i].chunk_begin = cb
+            cb += max(1, (w.numel() + chunk - 1) // chunk)
+        self.n, self.chunks = n, cb
+        self.numels = [w.numel() for w in weights]
+        self.d_table = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).to(self.dev)
+
+    def select(self, ranks, segmented, protect=None):
+        """0-based ascending ranks (one per segment) -> uint32 threshold keys on the device (int64 tensor view of uint32)."""
+        nseg = self.n if segmented else 1
+        assert len(ranks) == nseg
+        d_ranks = torch.tensor([int(r) for r in ranks], dtype=torch.int64, device=self.dev)
+        tkeys = torch.zeros(nseg, dtype=torch.int32, device=self.dev)
+        need = lib.ecf_workspace_bytes(_abi.OP_GLOBAL_SELECT, nseg, 0)
+        ws = _ws.get(self.dev, need, "global_select")
+        check(lib.ecf_global_select(self.d_table.data_ptr(), self.n, self.chunks, self.mode, self.n_batches, int(bool(segmented)),
+                                    0 if protect is None else protect.data_ptr(), d_ranks.data_ptr(), tkeys.data_ptr(),
+                                    ws.data_ptr(), ws.numel(), _stream(self.weights[0])))
+        return tkeys
+
+    def apply(self, tkeys, segmented, protect=None):
+        """w *= (score > threshold) in place; returns the per-tensor number of elements at or below the threshold."""
+        pruned = torch.zeros(self.n, dtype=torch.int64, device=self.dev)
+        check(lib.ecf_global_apply(self.d_table.data_ptr(), self.n, self.chunks, self.mode, self.n_batches, int(bool(segmented)),
+                                   0 if protect is None else protect.data_ptr(), tkeys.data_ptr(), pruned.data_ptr(),
+                                   _stream(self.weights[0])))
+        return pruned
+
+
+def global_key_to_float(key: int) -> float:
+    """Inverse of the kernels' order-preserving key (for reporting the threshold)."""
+    import struct
+
+    key &= 0xFFFFFFFF
+    bits = (key & 0x7FFFFFFF) if key & 0x80000000 else (~key & 0xFFFFFFFF)
+    return struct.unpack("<f", struct.pack("<I", bits))[0]
+
+
 def hessian_accum(x: torch.Tensor, H: torch.Tensor, alpha: float, beta: float) -> None:
     """H = beta*H + alpha * x^T x  on tcgen05 tensor cores (A8, sparsegpt_pruner.py:71-82)."""
     _require_cuda(x, H)

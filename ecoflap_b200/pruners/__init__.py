@@ -9,3 +9,7 @@ from .coop import (  # noqa: F401
     CLIPLayerSparseGPTPruner, CLIPLayerWandaPruner, TransformerLayerSparseGPTPruner, TransformerLayerWandaPruner,
 )
 from .upop import BertLayerWandaPruner, BLIPBertLayerWandaPruner  # noqa: F401
+from . import global_pruner  # noqa: F401
+from .global_pruner import (  # noqa: F401
+    BLIPT5GlobalGradMagAbsPruner, BLIPT5GlobalMagPruner, BLIPT5GlobalMeZoPruner, BLIPT5GlobalPruner,
+)

@@ -79,7 +79,8 @@ def test_host_mirror_keeps_the_reference_names():
     from ecoflap_b200 import registry
 
     for name in ("t5_wanda_pruner", "vit_wanda_pruner", "blipt5_wanda_pruner", "t5_sparsegpt_pruner",
-                 "vit_sparsegpt_pruner", "blipt5_sparsegpt_pruner"):
+                 "vit_sparsegpt_pruner", "blipt5_sparsegpt_pruner", "blipt5_global_mag_pruner",
+                 "blipt5_global_gradmagabs_pruner", "blipt5_global_mezo_pruner"):
         assert registry.registry.get_pruner_class(name) is not None, name
     from ecoflap_b200.pruners import coop, upop
 
@@ -99,4 +100,5 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith(".py"):
                 text = open(os.path.join(dirpath, f)).read()
-                assert "ecoflap_oracle" not in text and "c_oracle" not in text and "oracle/" not in text, os.path.join(dirpath, f)
+                assert ("ecoflap_oracle" not in text and "c_oracle" not in text and "oracle/" not in text
+                        and "aten_reference" not in text), os.path.join(dirpath, f)

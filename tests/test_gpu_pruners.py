@@ -342,3 +342,111 @@ def test_llama_prune_wanda_2_4_and_block_granularity():
     sizes = {k: v.numel() for k, v in m.named_parameters() if k in ratios}
     assert sum(ratios[k] * sizes[k] for k in ratios) / sum(sizes.values()) == pytest.approx(0.5, abs=2e-3)
     assert max(ratios.values()) <= 0.6 + 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ N3 global pruners
+def test_device_get_mask_matches_reference_fixture():
+    """get_mask / get_layerwise_mask on the device (csrc/global_select.cu) against masks from the unmodified reference
+    (tests/golden/global_mask.npz: protection on/off, heavy ties, zero rows).  The fixture's scores are fed through the
+    GRAD_ONLY mode (score = |G / 1|) over all-ones weights, so the surviving weights ARE the mask."""
+    from ecoflap_b200.pruners.global_pruner import device_get_mask_
+
+    g = np.load("tests/golden/global_mask.npz")
+    n = len(g["names"])
+    for case in range(4):
+        p, max_sp = float(g[f"c{case}__p"]), float(g[f"c{case}__max_sp"])
+        for segmented in (False, True):
+            params = [torch.nn.Parameter(torch.ones(g[f"c{case}__score{i}"].shape, device="cuda")) for i in range(n)]
+            grads = [torch.from_numpy(g[f"c{case}__score{i}"].copy()).cuda() for i in range(n)]
+            pruned = device_get_mask_(params, grads, 1, "grad_only", p, max_sp, segmented=segmented)
+            for i in range(n):
+                ref = g[f"c{case}__{'lw' if segmented else 'mask'}{i}"]
+                assert np.array_equal(params[i].data.cpu().numpy(), ref), (case, segmented, i)
+                assert int(pruned[i].item()) == int((ref == 0).sum())
+
+
+def test_device_get_mask_dtypes_signed_scores_and_the_empty_topk():
+    """Signed magnitude score on fp16 / bf16 / fp32 parameters against the oracle (orc.global_get_mask), sign bit kept on
+    pruned weights (w * 0.0), and the reference's IndexError when the target rounds to zero elements."""
+    import ecoflap_oracle as orc
+
+    from ecoflap_b200.pruners.global_pruner import device_get_mask_
+
+    torch.manual_seed(5)
+    for dt in (torch.float16, torch.bfloat16, torch.float32):
+        ws = [(torch.randn(shape) * 0.02).to(dt) for shape in ((40, 24), (7, 33), (128, 65))]
+        ws[1][0, :5] = 0.0
+        params = [torch.nn.Parameter(w.clone().cuda()) for w in ws]
+        device_get_mask_(params, None, 1, "mag", 0.4, 0.7)
+        want, _ = orc.global_get_mask({i: w.float().numpy() for i, w in enumerate(ws)}, 0.4, 0.7)
+        for i, (q, w) in enumerate(zip(params, ws)):
+            got = q.data.float().cpu().numpy()
+            assert np.array_equal(got, w.float().numpy() * want[i]), (dt, i)
+            assert np.array_equal(np.signbit(got), np.signbit(w.float().numpy() * want[i])), (dt, i)
+    with pytest.raises(IndexError):
+        device_get_mask_([torch.nn.Parameter(torch.ones(3, 3, device="cuda"))], None, 1, "mag", 0.05, 1.0)
+
+
+@pytest.mark.parametrize("tag,name,kw", [
+    ("mag_global3", "blipt5_global_mag_pruner", dict(is_global=True, iteration=3)),
+    ("mag_permodel", "blipt5_global_mag_pruner", dict(is_global=True, prune_per_model=True, iteration=1)),
+    ("mag_layerwise", "blipt5_global_mag_pruner", dict(is_global=False, iteration=2)),
+    ("gradmagabs_global2", "blipt5_global_gradmagabs_pruner", dict(is_global=True, iteration=2, num_samples=8)),
+])
+def test_global_pruners_match_reference(tag, name, kw):
+    """The registered global-pruner classes end to end (global_pruner.py:56-300) against the zero patterns the unmodified
+    reference produced on the same toy BLIP-2 (tests/gen_golden_global.py).  The magnitude variants depend on the weights
+    only -> bit-exact; the first-order variant depends on GPU-vs-CPU gradients -> near-threshold flips allowed."""
+    from ecoflap_b200.compression import load_pruner
+
+    g = np.load("tests/golden/global_e2e.npz")
+    torch.manual_seed(0)
+    m = cases.blip2_model().cuda()
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        p = load_pruner(name, m, cases.blip2_loader(), cfg=dict(
+            t5_prune_spec="2-0.5-1.0-1.0", vit_prune_spec="3-0.5-1.0-1.0", t5_pruning_method="x", vit_pruning_method="x", **kw))
+        model, sd = p.prune()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32
+    assert model is m and sd is None
+    checked = 0
+    for k, v in cases.prunable_state(m).items():
+        key = f"{tag}__{k}"
+        if key not in g.files:
+            continue
+        ref = np.unpackbits(g[key])[: v.size].reshape(v.shape).astype(bool)
+        if tag.startswith("mag"):
+            assert np.array_equal(v == 0, ref), k
+        else:
+            assert ((v == 0) == ref).mean() >= 0.995, (k, ((v == 0) == ref).mean())
+        checked += 1
+    assert checked >= 3 * 4 + 2 * 7 + 2 * 11  # every prunable Linear (+ the 2-D tensors the pruners leave dense)
+
+
+def test_real_score_method_matches_reference():
+    """score_method 'RealGradMagAbs_sum': the 3-iteration global pruning as a ratio oracle
+    (layer_single_base_pruner.py:183-245, 321-325) -- every parameter's zero fraction, weights restored afterwards."""
+    from ecoflap_b200.compression import load_pruner
+
+    g = np.load("tests/golden/global_e2e.npz")
+    torch.manual_seed(0)
+    m = cases.blip2_model().cuda()
+    before = {k: v.detach().clone() for k, v in m.named_parameters()}
+    p = load_pruner("blipt5_wanda_pruner", m, cases.blip2_loader(), cfg=dict(
+        t5_prune_spec="2-0.5-1.0-1.0", vit_prune_spec="3-0.5-1.0-1.0", t5_pruning_method="x", vit_pruning_method="x",
+        num_samples=16, sparsity_ratio_granularity="block", max_sparsity_per_layer=0.6, score_method="RealGradMagAbs_sum",
+        num_data_first_stage=8))
+    p.model_setup_and_record_attributes(m)
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        sd = p.get_sparsity(0.5, sparsity_ratio_granularity="block")
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32
+    keys = [str(k) for k in g["real__keys"]]
+    assert list(sd.keys()) == keys
+    np.testing.assert_allclose(np.array([sd[k] for k in keys]), g["real__vals"], rtol=0, atol=5e-3)
+    for k, v in m.named_parameters():
+        assert torch.equal(v.detach(), before[k]), k  # restored
