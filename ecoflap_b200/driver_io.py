@@ -33,13 +33,21 @@ def kept_parameter_percentage(model) -> float:
     return 100.0 * (total - zeros) / max(1, total)
 
 
-def save_pruning_outputs(model, job_id: str, sparsity_dict=None, start_time: Optional[float] = None, root: str = ".") -> Dict[str, str]:
-    """Write the three artefacts of ``--save_pruned_model`` (evaluate_blip.py:438-472).  Returns their paths."""
+def filter_eva_clip_checkpoint(state_dict):
+    """EVA-CLIP runs save only the visual tower without its last block (evaluate_eva_clip.py:414-423): BLIP-2 uses the
+    ViT-g's first 39 blocks, so ``blocks.39`` is dropped and everything outside ``visual.`` too."""
+    return {k: v for k, v in state_dict.items() if "blocks.39" not in k and "visual." in k}
+
+
+def save_pruning_outputs(model, job_id: str, sparsity_dict=None, start_time: Optional[float] = None, root: str = ".",
+                         eva_clip: bool = False) -> Dict[str, str]:
+    """Write the three artefacts of ``--save_pruned_model`` (evaluate_blip.py:438-472; ``eva_clip=True``: the filtered
+    checkpoint of evaluate_eva_clip.py:410-428).  Returns their paths."""
     out = {}
     folder = os.path.join(root, "pruned_checkpoint")
     os.makedirs(folder, exist_ok=True)
     out["checkpoint"] = os.path.join(folder, job_id + ".pth")
-    torch.save(model.state_dict(), out["checkpoint"])
+    torch.save(filter_eva_clip_checkpoint(model.state_dict()) if eva_clip else model.state_dict(), out["checkpoint"])
     print(out["checkpoint"])
     if sparsity_dict is not None and isinstance(sparsity_dict, dict):
         folder = os.path.join(root, "sparsity_dict")

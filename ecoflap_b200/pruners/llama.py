@@ -116,5 +116,28 @@ def prune_sparsegpt(args, model, tokenizer=None, device=torch.device("cuda:0"), 
     return _run(args, model, dataloader, device, prune_n, prune_m, "sparsegpt")
 
 
+def prune_magnitude(args, model, tokenizer=None, device=torch.device("cuda:0"), prune_n=0, prune_m=0):
+    """Magnitude baseline (LLaMA/main.py:8,76-77 -> upstream Wanda's lib/prune.py, absent from the reference checkout:
+    PARITY UNPINNED).  Upstream: per Linear  W_metric = |W|;  thresh = sort(W_metric.flatten())[int(numel * s)];
+    W[W_metric <= thresh] = 0  -- the per-layer threshold rule of A5 with a unit norm (fp32(|w|) * 1 orders and ties exactly
+    like the fp16 |w|), so it is the same fused kernel with scaler_row = 1; n:m takes the n:m kernel the same way."""
+    from .. import ops
+
+    layers = model.model.layers
+    for i in range(len(layers)):
+        subset = sweep.find_layers(layers[i])
+        items = []
+        for name in subset:
+            W = subset[name].weight.data
+            ones = torch.ones(W.shape[1], dtype=torch.float32, device=W.device)
+            if prune_n != 0:
+                ops.wanda_nm_select_apply(W, ones, int(prune_n), int(prune_m))
+            else:
+                items.append((W, ones, int(W.numel() * args.sparsity_ratio)))
+        for j in range(0, len(items), 8):  # the Linears of a block share launches (ECF_LAYER_MAX_BATCH = 8)
+            ops.wanda_layer_thresh_apply_batched(items[j:j + 8])
+    return model
+
+
 def check_sparsity(model):
     return sweep.check_sparsity(model, "model.layers")

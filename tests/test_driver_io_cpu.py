@@ -47,3 +47,22 @@ def test_pack_unpack_sparse_roundtrip():
         bits, vals = io.pack_sparse(W)
         assert bits.shape == (R, (C + 7) // 8) and vals.numel() == int((W != 0).sum())
         assert torch.equal(io.unpack_sparse(bits, vals, C), W)
+
+
+def test_eva_clip_checkpoint_filter(tmp_path):
+    """evaluate_eva_clip.py:414-423: only ``visual.*`` without ``blocks.39``."""
+    from ecoflap_b200 import driver_io as io
+
+    class Eva(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.visual = torch.nn.Module()
+            self.visual.blocks = torch.nn.ModuleList([torch.nn.Linear(4, 4) for _ in range(41)])
+            self.text = torch.nn.Linear(4, 4)
+
+    m = Eva()
+    kept = io.filter_eva_clip_checkpoint(m.state_dict())
+    assert all(k.startswith("visual.") for k in kept) and not any("blocks.39" in k for k in kept)
+    assert "visual.blocks.38.weight" in kept and "visual.blocks.40.weight" in kept and len(kept) == 2 * 40
+    out = io.save_pruning_outputs(m, "eva", root=str(tmp_path), eva_clip=True)
+    assert set(torch.load(out["checkpoint"])) == set(kept)

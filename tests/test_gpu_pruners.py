@@ -450,3 +450,22 @@ def test_real_score_method_matches_reference():
     np.testing.assert_allclose(np.array([sd[k] for k in keys]), g["real__vals"], rtol=0, atol=5e-3)
     for k, v in m.named_parameters():
         assert torch.equal(v.detach(), before[k]), k  # restored
+
+
+def test_llama_prune_magnitude_matches_aten_rule():
+    """prune_magnitude (LLaMA/main.py:76-77; upstream rule |W| <= sort(|W|.flatten())[int(numel*s)], PARITY UNPINNED):
+    bit-exact against the torch expression on the same fp16 weights."""
+    from ecoflap_b200.pruners import llama
+
+    m = cases.llama_model().cuda().half()
+    ref = {k: v.detach().clone() for k, v in m.model.layers.named_parameters() if v.dim() == 2}
+    llama.prune_magnitude(_llama_args(sparsity_ratio=0.4), m, None, torch.device("cuda:0"))
+    for k, v in m.model.layers.named_parameters():
+        if v.dim() != 2:
+            continue
+        W = ref[k]
+        metric = torch.abs(W)
+        thresh = torch.sort(metric.flatten())[0][int(W.numel() * 0.4)]
+        want = W.clone()
+        want[metric <= thresh] = 0
+        assert torch.equal(v.detach(), want), k
