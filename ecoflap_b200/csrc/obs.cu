@@ -19,6 +19,7 @@ namespace ecf {
 using namespace umma;
 
 constexpr int kObsBlock = 128;  // the only block size the kernels are specialised for
+constexpr int kObsSuper = 8 * kObsBlock;  // columns of a super-block: far trailing updates are deferred to its end (K = 1024)
 
 // ------------------------------------------------------------------ (i) tile threshold
 __device__ __forceinline__ uint32_t obs_key(float w, float d) {
@@ -75,7 +76,8 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------ (ii) sequential sweep, one warp per row
 __global__ void __launch_bounds__(256)
     obs_sweep_kernel(float* __restrict__ W, int64_t R, int64_t ldw, const float* __restrict__ Hinv, int64_t ldh, int i1, int count,
-                     const uint32_t* __restrict__ mask, __nv_bfloat16* __restrict__ err_hi, __nv_bfloat16* __restrict__ err_mid) {
+                     const uint32_t* __restrict__ mask, __nv_bfloat16* __restrict__ err_hi, __nv_bfloat16* __restrict__ err_mid,
+                     int err_ld, int err_col0) {
   extern __shared__ float hs[];  // Hinv1, [128][128], zero padded
   for (int e = threadIdx.x; e < kObsBlock * kObsBlock; e += 256) {
     const int i = e >> 7, j = e & 127;
@@ -118,8 +120,8 @@ __global__ void __launch_bounds__(256)
       const bool pruned = (m[s] >> lane) & 1u;
       if (c < count) wrow[c] = pruned ? 0.f : w[s];  // W[:, i1:i2] = Q1
       const __nv_bfloat16 h = __float2bfloat16_rn(e[s]);
-      err_hi[r * kObsBlock + c] = h;
-      err_mid[r * kObsBlock + c] = __float2bfloat16_rn(e[s] - __bfloat162float(h));
+      err_hi[r * err_ld + err_col0 + c] = h;  // this block's columns of the super-block's error matrix
+      err_mid[r * err_ld + err_col0 + c] = __float2bfloat16_rn(e[s] - __bfloat162float(h));
     }
   }
 }
@@ -132,10 +134,15 @@ constexpr int kTBTerm = (kTBN / 64) * kTBBox;         // 32 KB
 constexpr int kTStageBytes = 2 * kTATerm + 2 * kTBTerm;  // 96 KB
 constexpr int kTSmemBytes = kTStages * kTStageBytes + 1024 + 256;
 
+// W[:, n0 : n0 + ncols] -= Err[:, a_k0 : a_k0 + 64 nkb] * Hinv[h_row0 : h_row0 + 64 nkb, n0 : n0 + ncols]
 struct TrailParams {
   float* W;
   int64_t ldw;
-  int R, i1, i2, C;
+  int R;
+  int a_k0;    // first K column inside the super-block's error matrix
+  int nkb;     // K steps of 64 (2 = one 128-column block, 16 = a whole super-block)
+  int h_row0;  // Hinv row of the first K column
+  int n0, ncols;
   int MT, NT;
   int vec_ok;
 };
@@ -167,7 +174,7 @@ __global__ void __launch_bounds__(256, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int total_work = p.MT * p.NT;
-  constexpr int NKB = kObsBlock / kTBK;  // 2
+  const int NKB = p.nkb;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -179,13 +186,13 @@ __global__ void __launch_bounds__(256, 1)
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], kTStageBytes);
           uint8_t* st = smem + stage * kTStageBytes;
-          tma_load_2d(st, &ta_hi, &full_bar[stage], kb * kTBK, mi * kTBM);
-          tma_load_2d(st + kTATerm, &ta_mid, &full_bar[stage], kb * kTBK, mi * kTBM);
+          tma_load_2d(st, &ta_hi, &full_bar[stage], p.a_k0 + kb * kTBK, mi * kTBM);
+          tma_load_2d(st + kTATerm, &ta_mid, &full_bar[stage], p.a_k0 + kb * kTBK, mi * kTBM);
           uint8_t* b = st + 2 * kTATerm;
 #pragma unroll
           for (int j = 0; j < kTBN / 64; ++j) {
-            tma_load_2d(b + j * kTBBox, &tb_hi, &full_bar[stage], p.i2 + nj * kTBN + 64 * j, p.i1 + kb * kTBK);
-            tma_load_2d(b + kTBTerm + j * kTBBox, &tb_mid, &full_bar[stage], p.i2 + nj * kTBN + 64 * j, p.i1 + kb * kTBK);
+            tma_load_2d(b + j * kTBBox, &tb_hi, &full_bar[stage], p.n0 + nj * kTBN + 64 * j, p.h_row0 + kb * kTBK);
+            tma_load_2d(b + kTBTerm + j * kTBBox, &tb_mid, &full_bar[stage], p.n0 + nj * kTBN + 64 * j, p.h_row0 + kb * kTBK);
           }
           if (++stage == kTStages) { stage = 0; phase ^= 1; }
         }
@@ -226,13 +233,13 @@ __global__ void __launch_bounds__(256, 1)
     const int q = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int ncols = p.C - p.i2;
+    const int ncols = p.ncols;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const int nj = w / p.MT, mi = w - nj * p.MT;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int r = mi * kTBM + q * 32 + lane;
-      float* wrow = p.W + (int64_t)r * p.ldw + p.i2;
+      float* wrow = p.W + (int64_t)r * p.ldw + p.n0;
 #pragma unroll 1
       for (int chunk = 0; chunk < kTBN / 32; ++chunk) {
         uint32_t v[32];
@@ -305,8 +312,8 @@ static ObsWs obs_layout(void* ws, int64_t R, int64_t C) {
   o.hist = reinterpret_cast<unsigned*>(take(2048 * sizeof(unsigned)));
   o.mask = reinterpret_cast<uint32_t*>(take((size_t)R * 4 * sizeof(uint32_t)));
   const size_t rpad = (size_t)((R + kTBM - 1) / kTBM * kTBM);
-  o.err_hi = reinterpret_cast<__nv_bfloat16*>(take(rpad * kObsBlock * 2));
-  o.err_mid = reinterpret_cast<__nv_bfloat16*>(take(rpad * kObsBlock * 2));
+  o.err_hi = reinterpret_cast<__nv_bfloat16*>(take(rpad * kObsSuper * 2));
+  o.err_mid = reinterpret_cast<__nv_bfloat16*>(take(rpad * kObsSuper * 2));
   const size_t hb = (size_t)C * (size_t)round8(C) * 2;
   o.h_hi = reinterpret_cast<__nv_bfloat16*>(take(hb));
   o.h_mid = reinterpret_cast<__nv_bfloat16*>(take(hb));
@@ -360,10 +367,10 @@ extern "C" int ecf_obs_prune(float* W, int64_t R, int64_t C, int64_t ldw, const 
     obs_split_kernel<<<sms * 8, 256, 0, stream>>>(Hinv, C, (int)C, ldh, o.h_hi, o.h_mid, ldo);
     ECF_CUDA_OK(cudaGetLastError());
     const int64_t rpad = (R + kTBM - 1) / kTBM * kTBM;
-    ECF_CUDA_OK(cudaMemsetAsync(o.err_hi, 0, (size_t)rpad * kObsBlock * 2, stream));
-    ECF_CUDA_OK(cudaMemsetAsync(o.err_mid, 0, (size_t)rpad * kObsBlock * 2, stream));
-    if ((st = encode_tmap_2d(&ta_hi, o.err_hi, 2, ECF_BF16, kObsBlock, rpad, kObsBlock * 2, 64, kTBM)) != ECF_OK) return st;
-    if ((st = encode_tmap_2d(&ta_mid, o.err_mid, 2, ECF_BF16, kObsBlock, rpad, kObsBlock * 2, 64, kTBM)) != ECF_OK) return st;
+    ECF_CUDA_OK(cudaMemsetAsync(o.err_hi, 0, (size_t)rpad * kObsSuper * 2, stream));
+    ECF_CUDA_OK(cudaMemsetAsync(o.err_mid, 0, (size_t)rpad * kObsSuper * 2, stream));
+    if ((st = encode_tmap_2d(&ta_hi, o.err_hi, 2, ECF_BF16, kObsSuper, rpad, kObsSuper * 2, 64, kTBM)) != ECF_OK) return st;
+    if ((st = encode_tmap_2d(&ta_mid, o.err_mid, 2, ECF_BF16, kObsSuper, rpad, kObsSuper * 2, 64, kTBM)) != ECF_OK) return st;
     if ((st = encode_tmap_2d(&tb_hi, o.h_hi, 2, ECF_BF16, C, C, ldo * 2, 64, kTBK)) != ECF_OK) return st;
     if ((st = encode_tmap_2d(&tb_mid, o.h_mid, 2, ECF_BF16, C, C, ldo * 2, 64, kTBK)) != ECF_OK) return st;
   }
@@ -377,6 +384,8 @@ extern "C" int ecf_obs_prune(float* W, int64_t R, int64_t C, int64_t ldw, const 
     const int i1 = b * kObsBlock;
     const int i2 = (int)(i1 + kObsBlock < C ? i1 + kObsBlock : C);
     const int count = i2 - i1;
+    const int sb0 = i1 / kObsSuper * kObsSuper;                              // this block's super-block [sb0, sb1)
+    const int sb1 = (int)(sb0 + kObsSuper < C ? sb0 + kObsSuper : C);
     const int64_t elems = R * count;
     int64_t g = (elems + 255) / 256;
     if (g > (int64_t)sms * 8) g = (int64_t)sms * 8;
@@ -396,16 +405,25 @@ extern "C" int ecf_obs_prune(float* W, int64_t R, int64_t C, int64_t ldw, const 
       int64_t gs = (R + 7) / 8;
       if (gs > (int64_t)sms * 3) gs = (int64_t)sms * 3;
       obs_sweep_kernel<<<(unsigned)gs, 256, kObsBlock * kObsBlock * 4, stream>>>(W, R, ldw, Hinv, ldh, i1, count, o.mask, o.err_hi,
-                                                                                o.err_mid);
+                                                                                o.err_mid, kObsSuper, i1 - sb0);
     }
-    if (i2 < C && (phases & 4)) {
+    // Trailing update, two levels (the reference applies W[:, i2:] -= Err1 @ Hinv[i1:i2, i2:] after every block, :213; the
+    // sum over the blocks is the same, only its fp32 association differs): NEAR -- the rest of this 1024-column super-block,
+    // needed by its next block, K = 128; FAR -- everything behind the super-block, once, when its last block is done, with
+    // the errors of all eight blocks as one K = 1024 product (eight launch-bound K = 128 GEMMs over up to 6 000 columns
+    // become one that the tensor pipe can fill).
+    auto trailing = [&](int a_k0, int nkb, int h_row0, int n0, int ncols) {
       TrailParams p;
-      p.W = W; p.ldw = ldw; p.R = (int)R; p.i1 = i1; p.i2 = i2; p.C = (int)C;
+      p.W = W; p.ldw = ldw; p.R = (int)R; p.a_k0 = a_k0; p.nkb = nkb; p.h_row0 = h_row0; p.n0 = n0; p.ncols = ncols;
       p.MT = (int)((R + kTBM - 1) / kTBM);
-      p.NT = (int)((C - i2 + kTBN - 1) / kTBN);
-      p.vec_ok = (ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+      p.NT = (ncols + kTBN - 1) / kTBN;
+      p.vec_ok = (ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(W + n0) & 15) == 0);
       const int total = p.MT * p.NT;
       obs_trailing_kernel<<<total < sms ? total : sms, 256, kTSmemBytes, stream>>>(ta_hi, ta_mid, tb_hi, tb_mid, p);
+    };
+    if (phases & 4) {
+      if (i2 < sb1) trailing(i1 - sb0, kObsBlock / kTBK, i1, i2, sb1 - i2);
+      else if (sb1 < C) trailing(0, (sb1 - sb0) / kTBK, sb0, sb1, (int)C - sb1);
     }
     ECF_CUDA_OK(cudaGetLastError());
   }

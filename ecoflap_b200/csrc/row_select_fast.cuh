@@ -167,7 +167,7 @@ __device__ __forceinline__ void rf_mask_or(uint8_t* mask_row, uint32_t col) {
 }
 
 template <int DT, int NV, bool MULTI, int BLOCK, bool KEEP>
-__global__ void __launch_bounds__(BLOCK, (BLOCK == 256 ? ((NV <= 4 || !KEEP) ? 4 : 2) : 1))
+__global__ void __launch_bounds__(BLOCK, (BLOCK == 256 ? ((NV <= 4 || !KEEP) ? 3 : 2) : 1))
     row_select_fast_kernel(const __grid_constant__ RfBatch tb) {
   constexpr int NP = 4 * NV;  // packed pairs per lane
   constexpr bool F32 = (DT == ECF_F32);
