@@ -31,6 +31,74 @@ class _UniformSparsity:
         return self.ratio
 
 
+class _ReplayedLoss:
+    """The zeroth-order loop evaluates the SAME no-grad forward 2 * #layers times per first-stage batch (588 layers x 4
+    batches x 2 for BLIP-2); in eager mode each of those forwards is ~2 000 kernel launches issued by Python, and the GPU
+    idles behind the host.  The first evaluation of a batch is therefore captured in a CUDA graph (after two warm-up runs
+    on a side stream) and every later one is a replay: the same kernels on the same -- in place perturbed -- parameters,
+    hence the same losses, without the launch overhead.  The batch is moved to the device once, before the capture (a
+    pageable host-to-device copy cannot be captured).  Anything that cannot be captured (a model that synchronises or
+    allocates on the host inside its forward) makes this wrapper fall back to calling ``loss_func`` directly for the rest
+    of the run.  ECF_ZO_GRAPH=0 switches it off."""
+
+    def __init__(self, loss_func, model, device):
+        import os
+
+        self.loss_func, self.model, self.device = loss_func, model, device
+        self.enabled = (os.environ.get("ECF_ZO_GRAPH", "1") != "0" and torch.cuda.is_available()
+                        and torch.device(device).type == "cuda")
+        self._graphs = {}
+
+    @staticmethod
+    def _to_device(x, device):
+        if torch.is_tensor(x):
+            return x.to(device)
+        if isinstance(x, dict):
+            return {k: _ReplayedLoss._to_device(v, device) for k, v in x.items()}
+        if isinstance(x, (list, tuple)):
+            return type(x)(_ReplayedLoss._to_device(v, device) for v in x)
+        return x
+
+    def __call__(self, batch):
+        """-> (loss as a fresh 0-d tensor, batch_len)"""
+        if not self.enabled:
+            with torch.no_grad():
+                return self.loss_func(self.model, batch, self.device != "cpu")
+        entry = self._graphs.get(id(batch))
+        if entry is None and len(self._graphs) >= 64:
+            # a loader that builds new batch objects on every pass never hits the cache: stop capturing
+            print("[ecoflap_b200] zeroth-order loader yields fresh batch objects on every pass; running eagerly")
+            self.enabled = False
+            self._graphs.clear()
+            with torch.no_grad():
+                return self.loss_func(self.model, batch, self.device != "cpu")
+        if entry is None:
+            try:
+                dev_batch = self._to_device(batch, self.device)
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side), torch.no_grad():
+                    for _ in range(2):
+                        self.loss_func(self.model, dev_batch, True)
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                torch.cuda.synchronize(self.device)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph), torch.no_grad():
+                    loss, batch_len = self.loss_func(self.model, dev_batch, True)
+                entry = (graph, loss, int(batch_len), dev_batch, batch)  # (the batch is kept alive: ids are the keys)
+                self._graphs[id(batch)] = entry
+            except Exception as exc:  # not capturable: say so once, continue eagerly
+                print(f"[ecoflap_b200] zeroth-order forward not captured in a CUDA graph ({type(exc).__name__}: {exc}); running eagerly")
+                torch.cuda.synchronize(self.device)
+                self.enabled = False
+                self._graphs.clear()
+                with torch.no_grad():
+                    return self.loss_func(self.model, batch, self.device != "cpu")
+        graph, loss, batch_len = entry[0], entry[1], entry[2]
+        graph.replay()
+        return loss.clone(), batch_len
+
+
 class LayerSparsity:
     # Device the zeroth-order noise is drawn on.  None = the parameter's own device, which is what the reference does
     # (layer_single_base_pruner.py:479: CUDA Philox stream in a GPU run, mt19937 on CPU).  Setting "cpu" draws the
@@ -231,6 +299,7 @@ class LayerSparsity:
         device = next(iter(model.parameters())).device
         eps = self.noise_eps
         ghat = {k: 0.0 for k in names}
+        evaluate = _ReplayedLoss(loss_func, model, device)
         for i, (name, param) in enumerate(zip(names, params)):
             print(i, name)
             seen = 0
@@ -243,11 +312,9 @@ class LayerSparsity:
                         break
                     seed = np.random.randint(1000000000)
                     self.zo_perturb_parameters([param], random_seed=seed, scaling_factor=1, zo_eps=eps)
-                    with torch.no_grad():
-                        loss_plus, batch_len = loss_func(model, batch, device != "cpu")
+                    loss_plus, batch_len = evaluate(batch)
                     self.zo_perturb_parameters([param], random_seed=seed, scaling_factor=-2, zo_eps=eps)
-                    with torch.no_grad():
-                        loss_minus, batch_len = loss_func(model, batch, device != "cpu")
+                    loss_minus, batch_len = evaluate(batch)
                     # restore (inexact in fp16/bf16 exactly as in the reference)
                     self.zo_perturb_parameters([param], random_seed=seed, scaling_factor=1, zo_eps=eps)
                     seen += batch_len
@@ -288,6 +355,7 @@ class LayerSparsity:
             batch_lens.append(int(batch_len))
             seen += int(batch_len)
         draws = edist.zo_draws_per_layer(batch_lens, self.num_samples, self.num_noise)
+        evaluate = _ReplayedLoss(loss_func, model, device)
         seeds = [[int(np.random.randint(1000000000)) for _ in range(draws)] for _ in names]  # the reference's stream
         ghat_vec = torch.zeros(len(names), dtype=torch.float64, device=device)
         for i, (name, param) in enumerate(zip(names, params)):
@@ -305,11 +373,9 @@ class LayerSparsity:
                     seed = seeds[i][d]
                     d += 1
                     self.zo_perturb_parameters([param], random_seed=seed, scaling_factor=1, zo_eps=eps)
-                    with torch.no_grad():
-                        loss_plus, batch_len = loss_func(model, batch, device != "cpu")
+                    loss_plus, batch_len = evaluate(batch)
                     self.zo_perturb_parameters([param], random_seed=seed, scaling_factor=-2, zo_eps=eps)
-                    with torch.no_grad():
-                        loss_minus, batch_len = loss_func(model, batch, device != "cpu")
+                    loss_minus, batch_len = evaluate(batch)
                     self.zo_perturb_parameters([param], random_seed=seed, scaling_factor=1, zo_eps=eps)
                     seen += batch_len
                     acc += abs(((loss_plus - loss_minus) / (2 * eps)).item())
