@@ -41,7 +41,10 @@ __global__ void __launch_bounds__(kExThreads) norm_exchange_kernel(const __grid_
   if (tid == 0) s_epoch = my_flags[kExMaxWorld] + 1u;
   __syncthreads();
   const unsigned epoch = s_epoch;
-  const int64_t per = ((p.n + gridDim.x - 1) / gridDim.x + 3) & ~int64_t(3);
+  // The slicing depends on the STAGING size only, never on n: a CTA always owns the same index range of the halves and
+  // takes part in every call (with an empty slice when n is short), so all CTAs carry the same epoch and the parity
+  // argument above holds per CTA when vectors of different lengths share one staging buffer (round-1 advice).
+  const int64_t per = ((p.max_floats + gridDim.x - 1) / gridDim.x + 3) & ~int64_t(3);
   const int64_t i0 = min(p.n, (int64_t)cta * per), i1 = min(p.n, i0 + per);
   const int64_t half = (int64_t)(epoch & 1u) * p.max_floats;
   const bool vec = ((reinterpret_cast<uintptr_t>(p.local) & 15) == 0);  // staging halves are 16-byte aligned by contract
@@ -128,8 +131,8 @@ extern "C" int ecf_norm_exchange_p2p(float* local, int64_t n, void* const* peer_
     p.peer[r] = reinterpret_cast<float*>(peer_staging[r]);
   }
   p.local = local; p.n = n; p.max_floats = max_floats; p.rank = rank; p.world = world;
-  // a fixed CTA count per (staging buffer): the flags are per CTA, so every rank must use the same grid for the same n
-  int ctas = (int)((n + 4 * kExThreads - 1) / (4 * kExThreads));
+  // a fixed CTA count per staging buffer (a function of max_floats alone): flags and epochs are per CTA
+  int ctas = (int)((max_floats + 4 * kExThreads - 1) / (4 * kExThreads));
   if (ctas > kExMaxCtas) ctas = kExMaxCtas;
   if (ctas < 1) ctas = 1;
   norm_exchange_kernel<<<ctas, kExThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);

@@ -358,6 +358,7 @@ class LayerSparsity:
         evaluate = _ReplayedLoss(loss_func, model, device)
         seeds = [[int(np.random.randint(1000000000)) for _ in range(draws)] for _ in names]  # the reference's stream
         ghat_vec = torch.zeros(len(names), dtype=torch.float64, device=device)
+        mismatch = False
         for i, (name, param) in enumerate(zip(names, params)):
             if edist.zo_owner(i, world) != rank:
                 continue
@@ -380,8 +381,14 @@ class LayerSparsity:
                     seen += batch_len
                     acc += abs(((loss_plus - loss_minus) / (2 * eps)).item())
                 total += acc
-            assert d == draws, "the first-stage loader changed between passes"
+            if d != draws:
+                mismatch = True  # raised on EVERY rank after the collective below, never before it (no hang)
             ghat_vec[i] = total
+        flag = torch.tensor([1.0 if mismatch else 0.0], dtype=torch.float64, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if float(flag.item()) != 0.0:
+            raise RuntimeError("the first-stage loader yielded different batches on its second pass (shuffling loader?): "
+                               "the sharded zeroth-order loop needs a deterministic loader")
         dist.all_reduce(ghat_vec, op=dist.ReduceOp.SUM)
         for i, param in enumerate(params):  # every rank continues with the weights the single-GPU loop would leave
             dist.broadcast(param.data, src=edist.zo_owner(i, world))
