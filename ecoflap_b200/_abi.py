@@ -97,7 +97,7 @@ def _load():
         "ecf_zo_perturb": (i32, [vp, i32, i64, vp, f64, f64, vp]),
         "ecf_count_zero": (i32, [vp, i32, i64, vp, vp]),
         "ecf_hessian_accum": (i32, [vp, i32, i64, i64, i64, vp, i64, f32, f32, vp, sz, vp]),
-        "ecf_obs_prune": (i32, [vp, i64, i64, i64, vp, i64, C.POINTER(C.c_int64), i32, vp, sz, vp]),
+        "ecf_obs_prune": (i32, [vp, i64, i64, i64, vp, i64, C.POINTER(C.c_int64), i32, i32, i32, vp, sz, vp]),
         "ecf_global_chunk_elems": (i64, []),
         "ecf_global_select": (i32, [vp, i32, i64, i32, f64, i32, vp, vp, vp, vp, sz, vp]),
         "ecf_global_apply": (i32, [vp, i32, i64, i32, f64, i32, vp, vp, vp, vp]),

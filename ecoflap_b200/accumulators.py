@@ -229,8 +229,6 @@ class SparseGPT:
         return res
 
     def fasterprune(self, sparsity, prune_n=0, prune_m=0, blocksize=128, percdamp=0.01):
-        if prune_n != 0:
-            raise NotImplementedError("n:m sparsity is dead code in every shipped ECoFLaP recipe (prune_n = prune_m = 0)")
         W = self.layer.weight.data.clone()
         if isinstance(self.layer, nn.Conv2d):
             W = W.flatten(1)
@@ -243,7 +241,7 @@ class SparseGPT:
         for i1 in range(0, self.columns, blocksize):
             count = min(i1 + blocksize, self.columns) - i1
             kth.append(int(self.rows * count * sparsity))  # int(tmp.numel() * sparsity), :187
-        ops.obs_prune(W, Hinv, kth, blocksize)
+        ops.obs_prune(W, Hinv, kth, blocksize, prune_n, prune_m)
         if isinstance(self.layer, _Conv1D):
             W = W.t()
         self.layer.weight.data = W.reshape(self.layer.weight.shape).to(self.layer.weight.data.dtype)

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     obs_sweep_kernel(float* __restrict__ W, int64_t R, int64_t ldw, const float* __restrict__ Hinv, int64_t ldh, int i1, int count,
                      const uint32_t* __restrict__ mask, __nv_bfloat16* __restrict__ err_hi, __nv_bfloat16* __restrict__ err_mid,
-                     int err_ld, int err_col0) {
+                     int err_ld, int err_col0, int prune_n, int prune_m) {
   extern __shared__ float hs[];  // Hinv1, [128][128], zero padded
   for (int e = threadIdx.x; e < kObsBlock * kObsBlock; e += 256) {
     const int i = e >> 7, j = e & 127;
@@ -95,22 +95,54 @@ __global__ void __launch_bounds__(256)
       const int c = s * 32 + lane;
       w[s] = c < count ? wrow[c] : 0.f;
       e[s] = 0.f;
-      m[s] = mask[r * 4 + s];
+      m[s] = prune_n == 0 ? mask[r * 4 + s] : 0u;
     }
+    // one pruned column: its error, the rank-1 update of the columns behind it (warp-uniform control flow)
+    auto prune_column = [&](int s, int b) {
+      const int i = s * 32 + b;
+      const float wi = __shfl_sync(0xffffffffu, w[s], b);
+      const float err = __fdiv_rn(wi, hs[i * kObsBlock + i]);  // (w - q) / d with q = 0
+      if (lane == b) e[s] = err;
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      uint32_t bits = m[s];
-      while (bits) {  // warp-uniform: only pruned columns generate an error
-        const int b = __ffs(bits) - 1;
-        bits &= bits - 1;
-        const int i = s * 32 + b;
-        const float wi = __shfl_sync(0xffffffffu, w[s], b);
-        const float err = __fdiv_rn(wi, hs[i * kObsBlock + i]);  // (w - q) / d with q = 0
-        if (lane == b) e[s] = err;
+      for (int s2 = 0; s2 < 4; ++s2) {
+        const int c = s2 * 32 + lane;
+        if (s2 >= s && c >= i) w[s2] = __fsub_rn(w[s2], __fmul_rn(err, hs[i * kObsBlock + c]));  // W1[:, i:] -= err (x) Hinv1[i, i:]
+      }
+    };
+    if (prune_n == 0) {
 #pragma unroll
-        for (int s2 = 0; s2 < 4; ++s2) {
-          const int c = s2 * 32 + lane;
-          if (s2 >= s && c >= i) w[s2] = __fsub_rn(w[s2], __fmul_rn(err, hs[i * kObsBlock + c]));  // W1[:, i:] -= err (x) Hinv1[i, i:]
+      for (int s = 0; s < 4; ++s) {
+        uint32_t bits = m[s];
+        while (bits) {  // only pruned columns generate an error
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          prune_column(s, b);
+        }
+      }
+    } else {
+      // n:m (sparsegpt_pruner.py:195-198): when the sweep reaches column i with i % m == 0, the n smallest
+      // w^2 / diag(Hinv1)^2 of columns i .. i+m-1 -- computed from the weights AS UPDATED SO FAR -- are pruned (ties: lower
+      // column).  m divides 32, so a group lives in one 32-column segment; its lanes rank themselves with m shuffles.
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        m[s] = 0u;
+        for (int b0 = 0; b0 < 32 && s * 32 + b0 < count; b0 += prune_m) {
+          const int c = s * 32 + lane;
+          const float d = hs[(c < count ? c : 0) * kObsBlock + (c < count ? c : 0)];
+          const float t = c < count ? __fdiv_rn(__fmul_rn(w[s], w[s]), __fmul_rn(d, d)) : __int_as_float(0x7f800000);
+          int rank = 0;
+          for (int k = 0; k < prune_m; ++k) {
+            const float tk = __shfl_sync(0xffffffffu, t, b0 + k);
+            rank += (tk < t || (tk == t && b0 + k < lane)) ? 1 : 0;
+          }
+          const bool mine = lane >= b0 && lane < b0 + prune_m && c < count && rank < prune_n;
+          uint32_t bits = __ballot_sync(0xffffffffu, mine);
+          m[s] |= bits;
+          while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            prune_column(s, b);
+          }
         }
       }
     }
@@ -329,11 +361,14 @@ int encode_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, int dtype
 }  // namespace ecf
 
 extern "C" int ecf_obs_prune(float* W, int64_t R, int64_t C, int64_t ldw, const float* Hinv, int64_t ldh,
-                             const int64_t* kth_per_block, int blocksize, void* ws, size_t ws_bytes, ecf_stream_t stream_) {
+                             const int64_t* kth_per_block, int blocksize, int prune_n, int prune_m, void* ws, size_t ws_bytes,
+                             ecf_stream_t stream_) {
   using namespace ecf;
   int st = check_device();
   if (st != ECF_OK) return st;
-  ECF_REQUIRE(W != nullptr && Hinv != nullptr && kth_per_block != nullptr, ECF_ERR_INVALID, "obs_prune: null pointer");
+  ECF_REQUIRE(W != nullptr && Hinv != nullptr && (kth_per_block != nullptr || prune_n != 0), ECF_ERR_INVALID, "obs_prune: null pointer");
+  ECF_REQUIRE(prune_n == 0 || (prune_n > 0 && prune_n <= prune_m && prune_m <= 32 && 32 % prune_m == 0), ECF_ERR_INVALID,
+              "obs_prune: n:m = %d:%d unsupported (0 < n <= m, m a power of two <= 32)", prune_n, prune_m);
   ECF_REQUIRE(R > 0 && C > 0 && ldw >= C && ldh >= C, ECF_ERR_INVALID, "obs_prune: bad shape R=%lld C=%lld", (long long)R,
               (long long)C);
   ECF_REQUIRE(blocksize == kObsBlock, ECF_ERR_INVALID, "obs_prune: only blocksize 128 (the reference's value) is supported, got %d",
@@ -345,7 +380,7 @@ extern "C" int ecf_obs_prune(float* W, int64_t R, int64_t C, int64_t ldw, const 
   ObsWs o = obs_layout(ws, R, C);
   const int sms = sm_count();
   const int nblocks = (int)((C + kObsBlock - 1) / kObsBlock);
-  for (int b = 0; b < nblocks; ++b) {
+  for (int b = 0; b < nblocks && prune_n == 0; ++b) {
     const int64_t cnt = (b + 1 < nblocks) ? kObsBlock : C - (int64_t)b * kObsBlock;
     ECF_REQUIRE(kth_per_block[b] >= 0 && kth_per_block[b] < R * cnt, ECF_ERR_RANGE,
                 "obs_prune: kth index %lld out of range for the %lld-element tile of block %d (the reference raises IndexError)",
@@ -390,7 +425,7 @@ extern "C" int ecf_obs_prune(float* W, int64_t R, int64_t C, int64_t ldw, const 
     int64_t g = (elems + 255) / 256;
     if (g > (int64_t)sms * 8) g = (int64_t)sms * 8;
     const unsigned grid = (unsigned)g;
-    if (phases & 1) {
+    if ((phases & 1) && prune_n == 0) {  // (n:m: the mask is decided inside the sweep, from the updated weights)
       obs_hist_kernel<0><<<grid, 256, 0, stream>>>(W, R, ldw, Hinv, ldh, i1, count, o.state, o.hist);
       lt_scan_kernel<11, true><<<1, 1024, 0, stream>>>(o.state, o.hist, (unsigned long long)kth_per_block[b]);
       obs_hist_kernel<1><<<grid, 256, 0, stream>>>(W, R, ldw, Hinv, ldh, i1, count, o.state, o.hist);
@@ -401,11 +436,11 @@ extern "C" int ecf_obs_prune(float* W, int64_t R, int64_t C, int64_t ldw, const 
     if (phases & 2) {
       int64_t gm = (R * 4 + 7) / 8;
       if (gm > (int64_t)sms * 8) gm = (int64_t)sms * 8;
-      obs_mask_kernel<<<(unsigned)gm, 256, 0, stream>>>(W, R, ldw, Hinv, ldh, i1, count, o.state, o.mask);
+      if (prune_n == 0) obs_mask_kernel<<<(unsigned)gm, 256, 0, stream>>>(W, R, ldw, Hinv, ldh, i1, count, o.state, o.mask);
       int64_t gs = (R + 7) / 8;
       if (gs > (int64_t)sms * 3) gs = (int64_t)sms * 3;
       obs_sweep_kernel<<<(unsigned)gs, 256, kObsBlock * kObsBlock * 4, stream>>>(W, R, ldw, Hinv, ldh, i1, count, o.mask, o.err_hi,
-                                                                                o.err_mid, kObsSuper, i1 - sb0);
+                                                                                o.err_mid, kObsSuper, i1 - sb0, prune_n, prune_m);
     }
     // Trailing update, two levels (the reference applies W[:, i2:] -= Err1 @ Hinv[i1:i2, i2:] after every block, :213; the
     // sum over the blocks is the same, only its fp32 association differs): NEAR -- the rest of this 1024-column super-block,

@@ -365,16 +365,19 @@ def hessian_accum(x: torch.Tensor, H: torch.Tensor, alpha: float, beta: float) -
                                 float(beta), ws.data_ptr(), ws.numel(), _stream(x)))
 
 
-def obs_prune(W: torch.Tensor, Hinv: torch.Tensor, kth_per_block, blocksize: int = 128) -> None:
-    """SparseGPT block loop on an fp32 working copy W, in place (A10, sparsegpt_pruner.py:172-213)."""
+def obs_prune(W: torch.Tensor, Hinv: torch.Tensor, kth_per_block, blocksize: int = 128, prune_n: int = 0, prune_m: int = 0) -> None:
+    """SparseGPT block loop on an fp32 working copy W, in place (A10, sparsegpt_pruner.py:172-213); prune_n != 0 selects the
+    n:m branch (:182-198), where ``kth_per_block`` is ignored."""
     _require_cuda(W, Hinv)
     assert W.dtype == torch.float32 and Hinv.dtype == torch.float32
     R, C, ldw = _weight_2d(W)
     assert Hinv.shape == (C, C) and Hinv.stride(1) == 1
     nb = (C + blocksize - 1) // blocksize
+    if prune_n != 0:
+        kth_per_block = [0] * nb
     assert len(kth_per_block) == nb
     arr = (ctypes.c_int64 * nb)(*[int(v) for v in kth_per_block])
     need = lib.ecf_workspace_bytes(_abi.OP_OBS, R, C)
     ws = _ws.get(W.device, need, "obs")
-    check(lib.ecf_obs_prune(W.data_ptr(), R, C, ldw, Hinv.data_ptr(), Hinv.stride(0), arr, int(blocksize),
-                            ws.data_ptr(), ws.numel(), _stream(W)))
+    check(lib.ecf_obs_prune(W.data_ptr(), R, C, ldw, Hinv.data_ptr(), Hinv.stride(0), arr, int(blocksize), int(prune_n),
+                            int(prune_m), ws.data_ptr(), ws.numel(), _stream(W)))

@@ -89,8 +89,6 @@ class _Uniform:
 
 
 def _run(args, model, dataloader, device, prune_n, prune_m, method):
-    if prune_n != 0 and method != "wanda":
-        raise NotImplementedError("n:m SparseGPT (2:4 / 4:8) is not part of the ECoFLaP recipes")
     use_cache = getattr(model.config, "use_cache", None)
     if use_cache is not None:
         model.config.use_cache = False

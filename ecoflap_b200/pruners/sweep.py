@@ -222,8 +222,6 @@ def sweep_blocks(pruner, model, dataloader, device, spec: SweepSpec, model_prefi
                 f"{name}: accumulated {wrapped[name].nsamples} samples, expected {expected_nsamples}")
             print(f"pruning layer {i} name {name}")
             key = spec.sparsity_key(module_to_process, i, name)
-            if pruner.prune_n != 0 and method != "wanda":
-                raise NotImplementedError("n:m SparseGPT is dead code in the reference recipes (prune_n = prune_m = 0)")
             if method == "wanda" and pruner.prune_n != 0:
                 # structured n:m branch (wanda_pruner.py:265-270 / :546-551): same for the row and the layer variants
                 ops.wanda_nm_select_apply(subset[name].weight.data, wrapped[name].scaler_row, pruner.prune_n, pruner.prune_m)

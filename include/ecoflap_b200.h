@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ECF_ABI_VERSION 4 /* 2: batched per-row select, n:m select, peer-memory norm exchange; 3: cutoff-path per-layer select, flag offset; 4: global select / apply */
+#define ECF_ABI_VERSION 5 /* 2: batched per-row select, n:m select, peer-memory norm exchange; 3: cutoff-path per-layer select, flag offset; 4: global select / apply; 5: ecf_obs_prune takes n:m */
 
 #if defined(__GNUC__)
 #define ECF_API __attribute__((visibility("default")))
@@ -255,15 +255,18 @@ ECF_API int ecf_hessian_accum(const void* x, int x_dtype, int64_t T, int64_t C, 
                       float* H, int64_t ldh, float alpha, float beta,
                       void* ws, size_t ws_bytes, ecf_stream_t stream);
 
-/* A10 -- SparseGPT.fasterprune block loop, sparsegpt_pruner.py:172-213 (prune_n == 0).
+/* A10 -- SparseGPT.fasterprune block loop, sparsegpt_pruner.py:172-213.
  * W: [R, C] fp32 working copy (dead columns already zeroed), Hinv: [C, C] fp32 upper Cholesky
  * factor from the prologue (:96-163, cuSOLVER through torch.linalg).  For each `blocksize`-column
  * block: per-tile threshold at index kth_per_block[b] (= int(R*count*s), host-computed), the
- * in-block sequential OBS sweep, then the trailing update W[:, i2:] -= Err @ Hinv[i1:i2, i2:]. */
+ * in-block sequential OBS sweep, then the trailing update W[:, i2:] -= Err @ Hinv[i1:i2, i2:].
+ * prune_n != 0: the n:m branch (:182-198) -- no tile threshold; whenever the sweep reaches a column i with
+ * i % prune_m == 0 the prune_n smallest w^2 / diag(Hinv)^2 of columns i .. i+prune_m-1 (weights as updated so far) are
+ * pruned; prune_m must be a power of two <= 32; kth_per_block may be NULL. */
 ECF_API int ecf_obs_prune(float* W, int64_t R, int64_t C, int64_t ldw,
                   const float* Hinv, int64_t ldh,
                   const int64_t* kth_per_block /*host array, ceil(C/blocksize) entries*/,
-                  int blocksize, void* ws, size_t ws_bytes, ecf_stream_t stream);
+                  int blocksize, int prune_n, int prune_m, void* ws, size_t ws_bytes, ecf_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -274,8 +274,9 @@ def obs_prepare_hinv(H, percdamp=0.01, max_retry=100):
     return np.ascontiguousarray(L2.T), dead
 
 
-def obs_sweep(W, Hinv, sparsity, blocksize=128):
-    """fasterprune block loop -- sparsegpt_pruner.py:172-213 (prune_n == 0 branch).
+def obs_sweep(W, Hinv, sparsity, blocksize=128, prune_n=0, prune_m=0):
+    """fasterprune block loop -- sparsegpt_pruner.py:172-213 (prune_n == 0: per-tile threshold; prune_n != 0: the n:m
+    branch :195-198, decided column group by column group from the weights as updated so far, ties -> lower column).
 
     For each 128-column block: per-TILE threshold (same '<=' / +1 rule as the per-layer Wanda
     select), 128 sequential rank-1 updates inside the block, then the trailing update
@@ -291,10 +292,17 @@ def obs_sweep(W, Hinv, sparsity, blocksize=128):
         Err1 = np.zeros_like(W1)
         Hinv1 = Hinv[i1:i2, i1:i2]
         d = np.diag(Hinv1).reshape(1, -1)
-        tmp = (W1 ** 2 / d ** 2).astype(F32)
-        thresh = np.sort(tmp.reshape(-1), kind="stable")[int(tmp.size * sparsity)]
-        mask1 = tmp <= thresh
+        if prune_n == 0:
+            tmp = (W1 ** 2 / d ** 2).astype(F32)
+            thresh = np.sort(tmp.reshape(-1), kind="stable")[int(tmp.size * sparsity)]
+            mask1 = tmp <= thresh
+        else:
+            mask1 = np.zeros(W1.shape, dtype=bool)
         for i in range(count):
+            if prune_n != 0 and i % prune_m == 0:
+                tmp = (W1[:, i:i + prune_m] ** 2 / d[:, i:i + prune_m] ** 2).astype(F32)
+                idx = np.argsort(tmp, axis=1, kind="stable")[:, :prune_n]  # topk(largest=False)
+                np.put_along_axis(mask1[:, i:i + prune_m], idx, True, axis=1)
             w = W1[:, i]
             dd = Hinv1[i, i]
             q = w.copy()
@@ -309,12 +317,12 @@ def obs_sweep(W, Hinv, sparsity, blocksize=128):
     return W, mask_all
 
 
-def obs_prune(W, H, sparsity, blocksize=128, percdamp=0.01, out_dtype="fp32"):
-    """SparseGPT.fasterprune -- sparsegpt_pruner.py:84-218 (nn.Linear, prune_n == 0)."""
+def obs_prune(W, H, sparsity, blocksize=128, percdamp=0.01, out_dtype="fp32", prune_n=0, prune_m=0):
+    """SparseGPT.fasterprune -- sparsegpt_pruner.py:84-218 (nn.Linear)."""
     W = np.array(W, dtype=F32, copy=True)
     Hinv, dead = obs_prepare_hinv(H, percdamp)
     W[:, dead] = 0
-    Wp, mask = obs_sweep(W, Hinv, sparsity, blocksize)
+    Wp, mask = obs_sweep(W, Hinv, sparsity, blocksize, prune_n, prune_m)
     return round_to(Wp, out_dtype), mask
 
 

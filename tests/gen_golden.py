@@ -98,12 +98,14 @@ def gen_obs(ref):
     out = {}
     g = torch.Generator().manual_seed(3)
     cases = [
-        ("fp32_64x256_s40", "fp32", 64, 256, 0.4, False),
-        ("fp16_48x320_s50", "fp16", 48, 320, 0.5, False),  # ragged last block (320 = 2*128+64)
-        ("fp32_32x128_dead", "fp32", 32, 128, 0.5, True),  # dead column path
+        ("fp32_64x256_s40", "fp32", 64, 256, 0.4, False, 0, 0),
+        ("fp16_48x320_s50", "fp16", 48, 320, 0.5, False, 0, 0),  # ragged last block (320 = 2*128+64)
+        ("fp32_32x128_dead", "fp32", 32, 128, 0.5, True, 0, 0),  # dead column path
+        ("fp32_40x256_2of4", "fp32", 40, 256, 0.5, False, 2, 4),  # n:m branch (sparsegpt_pruner.py:195-198)
+        ("fp16_24x384_4of8", "fp16", 24, 384, 0.5, False, 4, 8),
     ]
     names = []
-    for name, dt, R, C, s, dead in cases:
+    for name, dt, R, C, s, dead, pn, pm in cases:
         layer = nn.Linear(C, R, bias=False)
         with torch.no_grad():
             layer.weight.copy_(torch.randn(R, C, generator=g) * 0.02)
@@ -118,8 +120,9 @@ def gen_obs(ref):
             acc.add_batch(x, None)
         out[f"{name}__H"] = acc.H.clone().numpy()
         out[f"{name}__W"] = f32(layer.weight.data)
-        acc.fasterprune(s, prune_n=0, prune_m=0, percdamp=0.01, blocksize=128)
+        acc.fasterprune(s, prune_n=pn, prune_m=pm, percdamp=0.01, blocksize=128)
         out[f"{name}__Wout"] = f32(layer.weight.data)
+        out[f"{name}__nm"] = np.array([pn, pm], dtype=np.int64)
         out[f"{name}__dtype"] = np.array(dt)
         out[f"{name}__s"] = np.float64(s)
         names.append(name)

@@ -682,8 +682,15 @@ def test_obs_prune_reference_golden():
         W[:, deadcols] = 0
         R, C = W.shape
         kth = [int(R * (min(i1 + 128, C) - i1) * s) for i1 in range(0, C, 128)]
+        pn, pm = (int(v) for v in g[f"{name}__nm"])
         Wd = torch.from_numpy(W).to(dev())
-        ops.obs_prune(Wd, torch.from_numpy(np.ascontiguousarray(Hinv)).to(dev()), kth)
+        ops.obs_prune(Wd, torch.from_numpy(np.ascontiguousarray(Hinv)).to(dev()), kth, prune_n=pn, prune_m=pm)
+        if pn:  # the n:m branch against the oracle's sweep on the same Hinv: identical decisions, 1e-3 weights
+            Wref, _ = orc.obs_sweep(W, Hinv, s, prune_n=pn, prune_m=pm)
+            gotf = f32(Wd)
+            assert ((gotf == 0) == (Wref == 0)).mean() >= 0.999, name
+            assert ((gotf.reshape(R, -1, pm) == 0).sum(-1) >= pn).all(), name
+            assert np.linalg.norm(gotf - Wref) / np.linalg.norm(Wref) < 5e-3, name
         got = orc.round_to(f32(Wd), dt)
         ref = g[f"{name}__Wout"]
         assert ((got == 0) == (ref == 0)).mean() >= 0.995, name
@@ -802,7 +809,8 @@ def test_prepare_hinv_reference_golden_end_to_end():
             lin.weight.copy_(torch.from_numpy(W).to(dev()))
         acc = SparseGPT(lin)
         acc.H = torch.from_numpy(H.copy()).to(dev())
-        acc.fasterprune(s, prune_n=0, prune_m=0, percdamp=0.01, blocksize=128)
+        pn, pm = (int(v) for v in g[f"{name}__nm"])
+        acc.fasterprune(s, prune_n=pn, prune_m=pm, percdamp=0.01, blocksize=128)
         got, ref = f32(lin.weight.data), g[f"{name}__Wout"]
         assert ((got == 0) == (ref == 0)).mean() >= 0.995, name
         assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 2e-2, name

@@ -120,8 +120,11 @@ def test_obs_prune_matches_reference(golden):
     for name in _cases(g):
         dt = str(g[f"{name}__dtype"])
         W, H, s = g[f"{name}__W"], g[f"{name}__H"], float(g[f"{name}__s"])
-        Wout, mask = orc.obs_prune(W, H, s, out_dtype=dt)
+        pn, pm = (int(v) for v in g[f"{name}__nm"])
+        Wout, mask = orc.obs_prune(W, H, s, out_dtype=dt, prune_n=pn, prune_m=pm)
         ref = g[f"{name}__Wout"]
+        if pn:  # n:m: exactly n zeros in every group of m
+            assert ((ref.reshape(ref.shape[0], -1, pm) == 0).sum(-1) >= pn).all(), name
         agree = ((Wout == 0) == (ref == 0)).mean()
         assert agree >= 0.995, (name, agree)
         rel = np.linalg.norm(Wout - ref) / np.linalg.norm(ref)
