@@ -6,9 +6,9 @@
 // Every rank owns a symmetric staging buffer (mapped into all peers; allocated and exchanged by the host through
 // torch's symmetric-memory rendezvous -- plumbing) laid out as  [2][max_floats] fp32 staging halves | flag words.
 // A CTA owns a slice of the vector and is independent of the other CTAs:
-//   1. copy the slice of the local vector into the staging half of this call's parity, __threadfence_system()
-//   2. store this call's epoch into flag[cta][my rank] of EVERY peer (remote stores over NVLink)
-//   3. spin (bounded) until flag[cta][r] >= epoch for every rank r in the local flags
+//   1. copy the slice of the local vector into the staging half of this call's parity, CTA barrier
+//   2. store-release (system scope) this call's epoch into flag[cta][my rank] of EVERY peer (remote stores over NVLink)
+//   3. spin (bounded) with load-acquire until flag[cta][r] >= epoch for every rank r in the local flags
 //   4. read the slice from every peer's staging half (volatile loads: NVLink, not cached), add in RANK ORDER -- all
 //      ranks compute bit-identical sums -- scale by 1/world, write the local vector in place
 // The epoch lives in device memory (flag[cta][world]) and is advanced by the kernel itself, so a CUDA-graph replay of
@@ -55,12 +55,14 @@ __global__ void __launch_bounds__(kExThreads) norm_exchange_kernel(const __grid_
   for (int64_t i = i0 + 4 * tid; i < v1; i += 4 * kExThreads)
     *reinterpret_cast<float4*>(mine + i) = *reinterpret_cast<const float4*>(p.local + i);
   for (int64_t i = v1 + tid; i < i1; i += kExThreads) mine[i] = p.local[i];
-  __threadfence_system();
   __syncthreads();
-  // 2. signal every peer (own flags included: the wait below is uniform)
+  // 2. signal every peer (own flags included: the wait below is uniform).  The flag store is a RELEASE at system scope
+  // issued after the CTA barrier: it is cumulative over the slice stores of all the CTA's threads (they happen before it
+  // through the barrier), which replaces a __threadfence_system() per thread -- the fence was the larger part of the
+  // exchange's ~20 us (round 2).
   if (tid < p.world) {
-    volatile unsigned* f = ex_flags(p.peer[tid], p.max_floats) + cta * kExFlagStride + p.rank;
-    *f = epoch;
+    unsigned* f = ex_flags(p.peer[tid], p.max_floats) + cta * kExFlagStride + p.rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
   }
   // 3. wait for every rank's slice (epochs only grow; wrap-around after 2^32 calls is not handled).  The wait is
   // bounded (~4 s of SM clocks): a peer that died must not leave this GPU spinning forever -- the slice is then
@@ -69,22 +71,24 @@ __global__ void __launch_bounds__(kExThreads) norm_exchange_kernel(const __grid_
   if (tid == 0) s_timeout = 0;
   __syncthreads();
   if (tid < p.world) {
-    volatile unsigned* f = my_flags + tid;
+    const unsigned* f = my_flags + tid;
     const long long t0 = clock64();
-    while ((int)(*f - epoch) < 0) {
+    for (;;) {  // ACQUIRE loads at system scope: pair with the peers' release stores
+      unsigned v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if ((int)(v - epoch) >= 0) break;
       if (clock64() - t0 > 8000000000ll) {
         s_timeout = 1;
         break;
       }
     }
   }
-  __syncthreads();
+  __syncthreads();  // the other threads' reads below happen after the acquires through this barrier
   if (s_timeout) {
     for (int64_t i = i0 + tid; i < i1; i += kExThreads) p.local[i] = __int_as_float(0x7fffffff);
     if (tid == 0) my_flags[kExMaxWorld] = epoch;
     return;
   }
-  __threadfence_system();
   // 4. rank-ordered sum of the peers' slices: all the remote 128-bit loads of a thread are in flight together
   const float inv = 1.0f / (float)p.world;
   for (int64_t i = i0 + 4 * tid; i < v1; i += 4 * kExThreads) {
