@@ -57,6 +57,20 @@ def parse():
     return ap.parse_args()
 
 
+def workload_config(summ):
+    """The `config` object, IDENTICAL in both arms (the driver compares them): what one step is, independent of who runs it."""
+    return {"workload": "BLIP-2 (EVA ViT-g + FlanT5-XL) Wanda 50% hot path, 128 samples / 16 batches of 8",
+            "arithmetic": "fp32 norms and scores over fp16 / bf16 weights and fp32 / fp16 / bf16 hook inputs",
+            "linears": summ["linears"], "params": summ["params"],
+            "algorithmic_bytes_per_step": summ["norm_bytes"] + summ["select_bytes"],
+            "hook_inputs": "q/k/v, wi_0/wi_1 and cross-attention k/v share one input tensor per block as in the model "
+                           f"(distinct norm input bytes per step {summ['unique_norm_input_bytes']})",
+            "l2": "GPU arm: inputs larger than L2 -- 47 GB touched per step, no buffer re-read within 126 MB (the per-kernel "
+                  "roofline timings flush L2 explicitly); reference arm: host memory",
+            "timing": "GPU arm: CUDA events per step, max over ranks, weights restored between steps outside the events; "
+                      "reference arm: perf_counter around the C/OpenMP calls"}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -202,9 +216,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / max(1, len(vals)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "BLIP-2 (EVA ViT-g + FlanT5-XL) Wanda 50% hot path, 128 samples / 16 batches of 8",
-                   "arithmetic": "fp32 norms and scores over fp16 / bf16 weights and fp32 / fp16 / bf16 hook inputs",
-                   "linears": summ["linears"], "params": summ["params"]},
+        "config": workload_config(summ),
         "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -507,8 +519,6 @@ def run_b200(args):
         for o in flat:
             o.W.copy_(o.W0)
 
-    side = [torch.cuda.Stream(device=dev) for _ in range(max(len(pb) for pb in lins))]
-
     ROW_SHARD = os.environ.get("ECF_ROW_SHARD", "0") == "1"  # row-sharded select + all-gather instead of replication
     # exchange step of the norms: our peer-memory kernel over NVSwitch (22 us per block at 8 GPUs) unless it is
     # unavailable or switched off (ECF_P2P_EXCHANGE=0), then one NCCL all-reduce per block (36 us at 8 GPUs)
@@ -523,9 +533,8 @@ def run_b200(args):
     def step_device(batches=range(N_BATCHES)):
         """one pass, everything resident in HBM (``batches``: the calibration batches this rank accumulates -- all 16 of its
         own shard under weak scaling, every world-th of the one fixed set under strong scaling).  Per block: the hook calls of its 16 calibration batches are
-        deferred into batched norm launches (<= 256 hook calls / 32 accumulators each), then the fused select of
-        every Linear; the selects of a block are independent, so each runs on its own stream and they overlap under
-        CUDA-graph replay."""
+        deferred into batched norm launches (<= 256 hook calls / 32 accumulators each), then the fused selects of the
+        block's Linears: one launch per select family (per-layer: all Linears; per-row: one per row length and dtype)."""
         main = torch.cuda.current_stream()
         for pb in lins:
             nb = NormBatch()
@@ -927,15 +936,9 @@ def run_b200(args):
             "metric": "calib_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BLIP-2 (EVA ViT-g + FlanT5-XL) Wanda 50% hot path, 128 samples / 16 batches of 8",
-                       "arithmetic": "fp32 norms and scores over fp16 / bf16 weights and fp32 / fp16 / bf16 hook inputs",
-                       "linears": summ["linears"], "params": summ["params"],
-                       "algorithmic_bytes_per_step": summ["norm_bytes"] + summ["select_bytes"],
-                       "hook_inputs": "q/k/v, wi_0/wi_1 and cross-attention k/v share one input tensor per block as in the model "
-                                      f"(distinct norm input bytes per step {summ['unique_norm_input_bytes']})",
-                       "l2": "inputs larger than L2: 47 GB touched per step, no buffer re-read within 126 MB",
-                       "timing": "CUDA events per step, max over ranks; weights restored between steps outside the events",
-                       "bracket_ms": bracket_ms, "launch": launch_mode, "parallelism": f"dp{world}: batch-sharded norms + " + ("peer-memory exchange kernel (NVSwitch P2P)" if pex is not None else "NCCL all-reduce") + " per block; select " + ("row-sharded + all-gather" if ROW_SHARD and world > 1 else "replicated per rank")},
+            "config": workload_config(summ),
+            "run": {"bracket_ms": bracket_ms, "launch": launch_mode,
+                    "parallelism": f"dp{world}: batch-sharded norms + " + ("peer-memory exchange kernel (NVSwitch P2P)" if pex is not None else "NCCL all-reduce") + " per block; select " + ("row-sharded + all-gather" if ROW_SHARD and world > 1 else "replicated per rank")},
             "prune_wall_s_hot_path": step_ms * 1e-3,
             "prune_wall_s": walls, "aten_gpu_baseline": aten, "strong_scaling": strong,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
