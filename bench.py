@@ -680,6 +680,8 @@ def run_b200(args):
     torch.cuda.synchronize()
 
     def timed_graph(fns, prepare=None, reps=3):
+        if prepare is not None:  # (the last timed step left the weights pruned: selecting them again would be the heavy-tie path)
+            prepare()
         for fn in fns:  # warm-up (workspaces, function attributes) outside the capture
             fn()
         torch.cuda.synchronize()
