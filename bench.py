@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--cpu-sample-s", type=float, default=15.0, help="target seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--prune-wall", default=os.environ.get("ECF_BENCH_PRUNE_WALL", "wanda,sparsegpt,ecoflap"),
+    ap.add_argument("--prune-wall", default=os.environ.get("ECF_BENCH_PRUNE_WALL", "wanda,sparsegpt,ecoflap,ecoflap_first"),
                     help="comma list of full-size BLIP-2 prune() runs to time (wanda, sparsegpt, ecoflap) or 'none'; "
                          "ecoflap = 4 704 BLIP-2 forwards, ~3 min on one B200")
     ap.add_argument("--no-sparsegpt-kernels", action="store_true")
@@ -254,6 +254,7 @@ def prune_wall(which=("wanda", "ecoflap"), verbose=False):
       ecoflap   zeroth-order stage 1 (MEZO-GradOnly_sum, block granularity, max 0.6, 32 first-stage samples: 588 layers x
                 4 batches x 2 forwards) + Wanda (reference: 5 985-6 115 s, ..._olmezo-gradient_sum0.6_block_nd32.yaml)
       sparsegpt blipt5_sparsegpt_pruner 50 %, batch size 1 as the reference asserts (reference: 802.63 s)
+      ecoflap_first first-order stage 1 (GradMagAbs_sum, 16 backward passes) + Wanda (reference: 450.31 s)
     Unlike the hot-path step this INCLUDES the model forwards (two per block and batch in stage 2, two per
     layer and batch in stage 1), i.e. mostly cuBLAS / SDPA time.  Under torchrun the calibration batches (stage 2) and the
     layers (stage 1) are sharded over the ranks; the wall time is the max over ranks."""
@@ -286,6 +287,9 @@ def prune_wall(which=("wanda", "ecoflap"), verbose=False):
         if name == "ecoflap":
             cfg.update(sparsity_ratio_granularity="block", max_sparsity_per_layer=0.6, score_method="MEZO-GradOnly_sum",
                        num_data_first_stage=32, num_noise=1, noise_eps=1e-3)
+        elif name == "ecoflap_first":  # LAVIS/scripts/blip2/ecoflap_first.py: GradMagAbs_sum, 128 first-stage samples
+            cfg.update(sparsity_ratio_granularity="block", max_sparsity_per_layer=0.6, score_method="GradMagAbs_sum",
+                       num_data_first_stage=128)
         elif name == "sparsegpt":
             reg = "blipt5_sparsegpt_pruner"
             loader = syn.blip2_full_loader(128, 1)
@@ -919,7 +923,7 @@ def run_b200(args):
     which = [w for w in args.prune_wall.split(",") if w and w != "none"]
     if which:
         walls = prune_wall(which)
-        ref_s = {"wanda": 240.16, "ecoflap": 5985.24, "sparsegpt": 802.63}
+        ref_s = {"wanda": 240.16, "ecoflap": 5985.24, "sparsegpt": 802.63, "ecoflap_first": 450.31}
         for k, v in walls.items():
             v["reference_wall_s"] = ref_s.get(k)
             v["reference_hardware"] = "one GPU, model unstated (LAVIS/training_statistics/*.yaml; BASELINE.md section 1)"

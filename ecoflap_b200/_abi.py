@@ -24,7 +24,7 @@ EXPORTED = (
     "ecf_layer_thresh_batched_workspace_bytes", "ecf_layer_thresh_flag_offset", "ecf_wanda_layer_thresh_apply_batched", "ecf_group_reduce_chunk_elems",
     "ecf_norm_exchange_staging_bytes", "ecf_norm_exchange_p2p",
     "ecf_group_abs_reduce", "ecf_zo_perturb", "ecf_count_zero", "ecf_hessian_accum", "ecf_obs_prune",
-    "ecf_global_chunk_elems", "ecf_global_select", "ecf_global_apply",
+    "ecf_global_chunk_elems", "ecf_global_select", "ecf_global_apply", "ecf_grad_accum", "ecf_global_score_sum",
 )
 
 
@@ -101,6 +101,8 @@ def _load():
         "ecf_global_chunk_elems": (i64, []),
         "ecf_global_select": (i32, [vp, i32, i64, i32, f64, i32, vp, vp, vp, vp, sz, vp]),
         "ecf_global_apply": (i32, [vp, i32, i64, i32, f64, i32, vp, vp, vp, vp]),
+        "ecf_grad_accum": (i32, [vp, vp, i32, i64, i32, vp]),
+        "ecf_global_score_sum": (i32, [vp, i32, i64, i32, f64, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

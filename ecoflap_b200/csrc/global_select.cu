@@ -194,6 +194,47 @@ __global__ void __launch_bounds__(kGsThreads)
   if (threadIdx.x == 0 && n_pruned != nullptr && s_cnt) atomicAdd(n_pruned + t, (unsigned long long)s_cnt);
 }
 
+// A13 / A14 -- per-tensor SUM of the per-element score (what LayerSparsity.return_sparsity reads of a first-order score
+// tensor, layer_single_base_pruner.py:361-370): fp32 partials per thread, fp64 per-CTA result, one fp64 atomic per chunk.
+template <int MODE>
+__global__ void __launch_bounds__(kGsThreads)
+    gs_sum_kernel(const ecf_global_desc* __restrict__ table, int n, float nb, double* __restrict__ sums) {
+  __shared__ int s_tensor;
+  __shared__ double s_part[kGsThreads / 32];
+  if (threadIdx.x == 0) s_tensor = gs_find_tensor(table, n, blockIdx.x);
+  __syncthreads();
+  const int t = s_tensor;
+  const ecf_global_desc d = table[t];
+  const int64_t begin = ((int64_t)blockIdx.x - d.chunk_begin) * kGsChunk;
+  const int64_t end = min(d.numel, begin + kGsChunk);
+  float acc = 0.f;
+  for (int64_t i = begin + threadIdx.x; i < end; i += kGsThreads) {
+    const float w = gs_load(d.W, d.dtype, i);
+    const float g = MODE == ECF_GLOBAL_MAG ? 0.f : d.G[i];
+    acc += gs_score<MODE>(w, g, nb);
+  }
+  double v = (double)acc;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < kGsThreads / 32; ++i) tot += s_part[i];
+    atomicAdd(sums + t, tot);
+  }
+}
+
+// G += |g| (or g^2): the device-side accumulation of the first-order loops (the reference adds the gradients up on the CPU
+// in fp32, layer_single_base_pruner.py:447-450, global_pruner.py:288)
+template <int DT>
+__global__ void __launch_bounds__(256) gs_grad_accum_kernel(float* __restrict__ G, const void* __restrict__ g, int64_t n, int square) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const float v = load_elem<DT>(g, i);
+    G[i] = __fadd_rn(G[i], square ? __fmul_rn(v, v) : fabsf(v));
+  }
+}
+
 size_t global_select_workspace_bytes(int64_t nseg) {
   return 256 + (size_t)nseg * (sizeof(LtState) + 2048 * sizeof(unsigned));
 }
@@ -261,6 +302,48 @@ extern "C" int ecf_global_apply(const ecf_global_desc* d_table, int n_tensors, i
     case ECF_GLOBAL_GRAD_MAG_ABS: gs_apply_kernel<ECF_GLOBAL_GRAD_MAG_ABS><<<chunks, kGsThreads, 0, s>>>(d_table, n_tensors, nb, segmented, d_protect, d_tkeys, d_n_pruned); break;
     case ECF_GLOBAL_GRAD_MAG_SQ: gs_apply_kernel<ECF_GLOBAL_GRAD_MAG_SQ><<<chunks, kGsThreads, 0, s>>>(d_table, n_tensors, nb, segmented, d_protect, d_tkeys, d_n_pruned); break;
     default: gs_apply_kernel<ECF_GLOBAL_GRAD_ONLY><<<chunks, kGsThreads, 0, s>>>(d_table, n_tensors, nb, segmented, d_protect, d_tkeys, d_n_pruned); break;
+  }
+  ECF_CUDA_OK(cudaGetLastError());
+  return ECF_OK;
+}
+
+extern "C" int ecf_global_score_sum(const ecf_global_desc* d_table, int n_tensors, int64_t total_chunks, int mode, double n_batches,
+                                    double* d_sums, ecf_stream_t stream) {
+  using namespace ecf;
+  int st = check_device();
+  if (st != ECF_OK) return st;
+  ECF_REQUIRE(d_table != nullptr && d_sums != nullptr, ECF_ERR_INVALID, "global_score_sum: null pointer");
+  ECF_REQUIRE(n_tensors >= 1 && total_chunks >= n_tensors && total_chunks < (1ll << 31), ECF_ERR_INVALID,
+              "global_score_sum: bad table size n=%d chunks=%lld", n_tensors, (long long)total_chunks);
+  ECF_REQUIRE(mode >= ECF_GLOBAL_MAG && mode <= ECF_GLOBAL_GRAD_ONLY, ECF_ERR_INVALID, "global_score_sum: unknown score mode %d", mode);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const float nb = (float)n_batches;
+  const unsigned chunks = (unsigned)total_chunks;
+  switch (mode) {
+    case ECF_GLOBAL_MAG: gs_sum_kernel<ECF_GLOBAL_MAG><<<chunks, kGsThreads, 0, s>>>(d_table, n_tensors, nb, d_sums); break;
+    case ECF_GLOBAL_GRAD_MAG_ABS: gs_sum_kernel<ECF_GLOBAL_GRAD_MAG_ABS><<<chunks, kGsThreads, 0, s>>>(d_table, n_tensors, nb, d_sums); break;
+    case ECF_GLOBAL_GRAD_MAG_SQ: gs_sum_kernel<ECF_GLOBAL_GRAD_MAG_SQ><<<chunks, kGsThreads, 0, s>>>(d_table, n_tensors, nb, d_sums); break;
+    default: gs_sum_kernel<ECF_GLOBAL_GRAD_ONLY><<<chunks, kGsThreads, 0, s>>>(d_table, n_tensors, nb, d_sums); break;
+  }
+  ECF_CUDA_OK(cudaGetLastError());
+  return ECF_OK;
+}
+
+extern "C" int ecf_grad_accum(float* G, const void* g, int g_dtype, int64_t numel, int square, ecf_stream_t stream) {
+  using namespace ecf;
+  int st = check_device();
+  if (st != ECF_OK) return st;
+  ECF_REQUIRE(G != nullptr && g != nullptr && numel >= 0, ECF_ERR_INVALID, "grad_accum: null pointer");
+  ECF_REQUIRE(g_dtype >= ECF_F32 && g_dtype <= ECF_BF16, ECF_ERR_INVALID, "grad_accum: unknown dtype %d", g_dtype);
+  if (numel == 0) return ECF_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int64_t grid = (numel + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (grid > cap) grid = cap;
+  switch (g_dtype) {
+    case ECF_F32: gs_grad_accum_kernel<ECF_F32><<<(unsigned)grid, 256, 0, s>>>(G, g, numel, square); break;
+    case ECF_F16: gs_grad_accum_kernel<ECF_F16><<<(unsigned)grid, 256, 0, s>>>(G, g, numel, square); break;
+    default: gs_grad_accum_kernel<ECF_BF16><<<(unsigned)grid, 256, 0, s>>>(G, g, numel, square); break;
   }
   ECF_CUDA_OK(cudaGetLastError());
   return ECF_OK;

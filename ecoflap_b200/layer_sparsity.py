@@ -266,6 +266,16 @@ class LayerSparsity:
                 params.append(v)
         return names, params
 
+    def _grad_accumulate(self, G, grads, square):
+        """G += |g| (or g^2) per parameter, fp32, on the device: ecf_grad_accum."""
+        for g_acc, gr in zip(G, grads):
+            ops.grad_accum(g_acc, gr.detach(), square=square)
+
+    def _score_sums(self, params, G, n_batches, mode):
+        """sum over the elements of the first-order score per parameter as a float64 vector: ecf_global_score_sum."""
+        datas = [p.data if p.data.is_contiguous() else p.data.contiguous() for p in params]
+        return ops.GlobalTable(datas, G, n_batches, mode).score_sums()
+
     def _magnitude_sums(self, params):
         """(sum|w|, sum w^2) per parameter as python floats: one kernel launch over all tensors."""
         sa, sq = ops.group_abs_reduce([p.data for p in params])
@@ -419,7 +429,8 @@ class LayerSparsity:
         model, loss_func = self.model, self.loss_func
         names, params = self._selected(layer_to_group_mapping)
         device = next(iter(model.parameters())).device
-        acc = {k: None for k in names}
+        square = self.score_compute == "GradMagSquare"
+        G = [torch.zeros(p.shape, dtype=torch.float32, device=p.device) for p in params]  # sum of |g| (g^2), on the device
         seen, nbatches = 0, 0
         # P ranks: data parallel over the first-stage batches, rank r takes batch j = r (mod P).  Every
         # score is linear in the per-batch |g| (or g^2) terms, so the ranks exchange one scalar per layer at the end
@@ -437,32 +448,25 @@ class LayerSparsity:
             nbatches += 1
             grads = torch.autograd.grad(loss, params)
             assert len(grads) == len(names) == len(params)
-            for k, gr in zip(names, grads):
-                gr = gr.detach().float()
-                term = gr * gr if self.score_compute == "GradMagSquare" else gr.abs()
-                acc[k] = term if acc[k] is None else acc[k].add_(term)
-        scores = {}
-        for k, p in zip(names, params):
-            if acc[k] is None:  # this rank saw no batch (more ranks than batches)
-                acc[k] = torch.zeros_like(p, dtype=torch.float32)
-            gbar = acc[k] / nbatches
-            w = p.detach().float()
-            if "GradMagSquare" in self.score_compute:
-                s = (w * w * gbar).sum()
-            elif "GradMagAbs" in self.score_compute:
-                s = (w.abs() * gbar.abs()).sum()
-            elif "GradOnly" in self.score_compute:
-                s = gbar.abs().sum()
-            else:
-                raise ValueError(f"unknown first-order score method {self.score_compute!r}")
-            scores[k] = s.reshape(1)
+            self._grad_accumulate(G, grads, square)
+        if "GradMagSquare" in self.score_compute:
+            mode = "grad_mag_sq"
+        elif "GradMagAbs" in self.score_compute:
+            mode = "grad_mag_abs"
+        elif "GradOnly" in self.score_compute:
+            mode = "grad_only"
+        else:
+            raise ValueError(f"unknown first-order score method {self.score_compute!r}")
+        # sum over the elements of |W| * |G / nb|  (W^2 * G / nb, |G / nb|): one segmented-reduction launch over all the
+        # layers (ecf_global_score_sum); the per-element score tensors of the reference (:463-469) are never built
+        vec = self._score_sums(params, G, max(1, nbatches), mode)
+        del G
         if world > 1:
             import torch.distributed as dist
 
-            vec = torch.cat([scores[k].double() for k in names])
             dist.all_reduce(vec, op=dist.ReduceOp.SUM)
-            scores = {k: vec[i:i + 1].float() for i, k in enumerate(names)}
-        return {k: v.cpu() for k, v in scores.items()}
+        vec = vec.float().cpu()
+        return {k: vec[i:i + 1].clone() for i, k in enumerate(names)}
 
     def _batch_len(self, batch, device):
         """Length of a first-stage batch this rank does not evaluate (the stopping rule counts every batch): the

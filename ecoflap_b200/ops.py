@@ -335,6 +335,13 @@ class GlobalTable:
                                     ws.data_ptr(), ws.numel(), _stream(self.weights[0])))
         return tkeys
 
+    def score_sums(self):
+        """Per-tensor sum of the per-element score as a float64 CUDA tensor (one launch for the whole table)."""
+        sums = torch.zeros(self.n, dtype=torch.float64, device=self.dev)
+        check(lib.ecf_global_score_sum(self.d_table.data_ptr(), self.n, self.chunks, self.mode, self.n_batches, sums.data_ptr(),
+                                       _stream(self.weights[0])))
+        return sums
+
     def apply(self, tkeys, segmented, protect=None):
         """w *= (score > threshold) in place; returns the per-tensor number of elements at or below the threshold."""
         pruned = torch.zeros(self.n, dtype=torch.int64, device=self.dev)
@@ -342,6 +349,14 @@ class GlobalTable:
                                    0 if protect is None else protect.data_ptr(), tkeys.data_ptr(), pruned.data_ptr(),
                                    _stream(self.weights[0])))
         return pruned
+
+
+def grad_accum(G: torch.Tensor, g: torch.Tensor, square: bool = False) -> None:
+    """G += |g| (or g^2) in place, G fp32 (A13: the first-order loops' gradient accumulator, kept on the device)."""
+    _require_cuda(G, g)
+    assert G.dtype == torch.float32 and G.is_contiguous() and G.numel() == g.numel()
+    g = g if g.is_contiguous() else g.contiguous()
+    check(lib.ecf_grad_accum(G.data_ptr(), g.data_ptr(), dtype_code(g), g.numel(), int(bool(square)), _stream(G)))
 
 
 def global_key_to_float(key: int) -> float:

@@ -41,8 +41,7 @@ def accumulate_abs_grads(model, data_loader, loss_func, names, params, num_sampl
         grads = torch.autograd.grad(loss, params)
         assert len(grads) == len(names) == len(params)
         for g_acc, g in zip(G, grads):
-            g = g.detach().float()
-            g_acc.add_(g * g if square else g.abs())
+            ops.grad_accum(g_acc, g.detach(), square=square)  # G += |g| (g^2): ecf_grad_accum
     return G, nb
 
 

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ECF_ABI_VERSION 5 /* 2: batched per-row select, n:m select, peer-memory norm exchange; 3: cutoff-path per-layer select, flag offset; 4: global select / apply; 5: ecf_obs_prune takes n:m */
+#define ECF_ABI_VERSION 6 /* 2: batched per-row select, n:m select, peer-memory norm exchange; 3: cutoff-path per-layer select, flag offset; 4: global select / apply; 5: ecf_obs_prune takes n:m; 6: first-order accumulate / score sums */
 
 #if defined(__GNUC__)
 #define ECF_API __attribute__((visibility("default")))
@@ -234,6 +234,15 @@ ECF_API int ecf_global_select(const ecf_global_desc* d_table, int n_tensors, int
 ECF_API int ecf_global_apply(const ecf_global_desc* d_table, int n_tensors, int64_t total_chunks, int mode, double n_batches,
                      int segmented, const uint32_t* d_protect, const uint32_t* d_tkeys, unsigned long long* d_n_pruned,
                      ecf_stream_t stream);
+
+/* A13 -- first-order scores, layer_single_base_pruner.py:416-471 (global_pruner.py:256-300).
+ * ecf_grad_accum:  G += |g| (square == 0) or g^2, G fp32, g in the parameter dtype -- replaces the per-batch
+ *   `gradients_dict[k] += v.cpu().data.float().abs()` (:447-450) with a device-resident accumulator.
+ * ecf_global_score_sum:  d_sums[t] += sum over the elements of tensor t of the per-element score (same table and score
+ *   modes as ecf_global_select) -- all return_sparsity (:361-370) reads of a first-order score tensor; d_sums: fp64 [n]. */
+ECF_API int ecf_grad_accum(float* G, const void* g, int g_dtype, int64_t numel, int square, ecf_stream_t stream);
+ECF_API int ecf_global_score_sum(const ecf_global_desc* d_table, int n_tensors, int64_t total_chunks, int mode, double n_batches,
+                         double* d_sums, ecf_stream_t stream);
 
 /* A11 -- LayerSparsity.zo_perturb_parameters, layer_single_base_pruner.py:473-486.
  *   w = rn(w + rn(rn(scaling * z) * eps)), each rounding in the parameter dtype (torch evaluates

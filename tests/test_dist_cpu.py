@@ -155,7 +155,7 @@ def _zo_worker(rank, world, port, out_dir):
     from ecoflap_b200.layer_sparsity import LayerSparsity
 
     class CpuLayerSparsity(LayerSparsity):
-        """Host logic under test; the two CUDA kernels are replaced by the reference's own expressions."""
+        """Host logic under test; the CUDA kernels are replaced by the reference's own expressions."""
 
         def zo_perturb_parameters(self, params, random_seed=1, scaling_factor=1, zo_eps=1e-3):
             torch.manual_seed(random_seed)  # layer_single_base_pruner.py:473-486
@@ -165,6 +165,18 @@ def _zo_worker(rank, world, port, out_dir):
 
         def _magnitude_sums(self, params):
             return [float(p.data.abs().sum()) for p in params], [float((p.data ** 2).sum()) for p in params]
+
+        def _grad_accumulate(self, G, grads, square):  # layer_single_base_pruner.py:447-450
+            for g_acc, gr in zip(G, grads):
+                g_acc.add_(gr.detach().float() ** 2 if square else gr.detach().float().abs())
+
+        def _score_sums(self, params, G, n_batches, mode):  # :463-469, summed
+            out = []
+            for p_, g_ in zip(params, G):
+                gbar, w = g_ / n_batches, p_.data.float()
+                s_ = {"grad_mag_sq": w ** 2 * gbar, "grad_mag_abs": w.abs() * gbar.abs(), "grad_only": gbar.abs()}[mode]
+                out.append(s_.double().sum())
+            return torch.stack(out)
 
     def make_model():
         torch.manual_seed(0)
