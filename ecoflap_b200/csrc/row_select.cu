@@ -310,6 +310,8 @@ static int run_row_select(void* W, int64_t R, int64_t C, int64_t ld, const float
 int row_select_fast_f16(RfBatch&, int, bool, cudaStream_t);
 int row_select_fast_bf16(RfBatch&, int, bool, cudaStream_t);
 int row_select_fast_f32(RfBatch&, int, bool, cudaStream_t);
+int row_select_tma_f16(RfBatch&, int, cudaStream_t);
+int row_select_tma_bf16(RfBatch&, int, cudaStream_t);
 
 // tuning / A-B switches (read once): ECF_RS_NVMAX = vectors per lane cap of the fast kernel (1..8),
 // ECF_RS_KEEP=0 makes 16-bit rows with > 4 vectors per lane re-read the weights in the apply pass (fewer registers),
@@ -331,6 +333,12 @@ static int rs_check(const ecf_row_desc& d, int i) {
   ECF_REQUIRE(d.mask_bits == nullptr || d.mask_ld >= (d.C + 7) / 8, ECF_ERR_INVALID, "row_select: mask_ld too small (matrix %d)", i);
   ECF_REQUIRE(d.dtype >= 0 && d.dtype <= 2, ECF_ERR_INVALID, "row_select: unknown dtype %d (matrix %d)", d.dtype, i);
   return ECF_OK;
+}
+
+// the bulk-copy kernel (row_select_tma.cuh): 16-bit weights, whole 256-column tiles, no mask / zero-count outputs
+static bool rs_tma_ok(const ecf_row_desc& d) {
+  return d.dtype != ECF_F32 && (d.C == 768 || d.C == 1024 || d.C == 2048 || d.C == 3072 || d.C == 4096 || d.C == 5120) &&
+         (d.ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(d.W) & 15) == 0) && d.mask_bits == nullptr && d.n_zero == nullptr;
 }
 
 static bool rs_fast_ok(const ecf_row_desc& d) {
@@ -358,6 +366,7 @@ extern "C" int ecf_wanda_row_select_apply_batched(const ecf_row_desc* descs, int
   static const bool force_generic = rs_env("ECF_RS_GENERIC", 0) != 0;
   static const bool keep = rs_env("ECF_RS_KEEP", 1) != 0;
   static const int prefetch = rs_env("ECF_RS_PREFETCH", 0);
+  static const int tma = rs_env("ECF_RS_TMA", 1);  // 0: round-2 kernels only; 1 / 2: bulk-copy kernel with that many stages (C <= 2048)
   bool done[ECF_ROW_MAX_BATCH];
   for (int i = 0; i < n; ++i) done[i] = descs[i].R == 0;
   for (int i = 0; i < n; ++i) {
@@ -375,19 +384,25 @@ extern "C" int ecf_wanda_row_select_apply_batched(const ecf_row_desc* descs, int
       done[i] = true;
       continue;
     }
-    // every remaining matrix with this row length and dtype joins the launch
+    // every remaining matrix with this row length and dtype (and the same kernel) joins the launch
+    const bool use_tma = tma != 0 && rs_tma_ok(d0);
     RfBatch tb;
     tb.n = 0;
     tb.C = (int)d0.C;
     tb.prefetch = prefetch;
     for (int j = i; j < n; ++j) {
       const ecf_row_desc& d = descs[j];
-      if (done[j] || d.C != d0.C || d.dtype != d0.dtype || !rs_fast_ok(d)) continue;
+      if (done[j] || d.C != d0.C || d.dtype != d0.dtype || !rs_fast_ok(d) || (tma != 0 && rs_tma_ok(d)) != use_tma) continue;
       RfMat& M = tb.m[tb.n++];
       M.W = d.W; M.s = d.scaler_row; M.mask = d.mask_bits; M.n_zero = d.n_zero; M.R = d.R; M.ld = d.ld; M.mask_ld = d.mask_ld;
       M.k = (int)(d.k_per_row > d.C ? d.C : d.k_per_row);
       M.batch_begin = 0;
       done[j] = true;
+    }
+    if (use_tma) {
+      st = d0.dtype == ECF_F16 ? row_select_tma_f16(tb, tma, s) : row_select_tma_bf16(tb, tma, s);
+      if (st != ECF_OK) return st;
+      continue;
     }
     switch (d0.dtype) {
       case ECF_F32: st = row_select_fast_f32(tb, nv_max, keep, s); break;

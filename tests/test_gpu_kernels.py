@@ -348,6 +348,100 @@ def test_row_select_batched_equals_single_calls():
         ops.wanda_row_select_apply_batched([(batched[0], ss[0], 1), (batched[0], ss[0], 1)])
 
 
+# the bulk-copy kernel (row_select_tma.cuh) serves 16-bit rows of whole 256-column tiles when no mask / zero count is asked for
+TMA_C = [768, 1024, 2048, 3072, 4096, 5120]
+
+
+@pytest.mark.parametrize("dt", ["fp16", "bf16"])
+@pytest.mark.parametrize("C", TMA_C)
+def test_row_select_bulk_copy_kernel_bit_exact(dt, C):
+    """Enough rows that every warp carries its bracket over several rows; row scales that jump by orders of magnitude,
+    constant / zero / half-pruned rows in between (the carried guess is then wrong and must only cost time)."""
+    from ecoflap_b200 import ops
+
+    R = 1300 if C <= 2048 else 520
+    W = synth_w(R, C, dt, seed=3 * C + 1)
+    g = torch.Generator().manual_seed(C)
+    scale = torch.where(torch.rand(R, generator=g) < 0.2, torch.tensor(50.0), torch.tensor(1.0))
+    W = (W.float() * scale[:, None]).to(TD[dt])
+    W[7] = 0
+    W[8, ::2] = 0
+    W[9] = W[9, 3]
+    W[10, : C // 2] = W[10, C // 2:]
+    W[11, C // 3:] = 0
+    W[40:60] = (W[40:60].float() * 1e-3).to(TD[dt])
+    s = synth_norm(C, seed=C + 9)
+    sd = torch.from_numpy(s).to(dev())
+    for sparsity in (0.5, 0.5199999809265137, 0.3, 0.9, 0.0, 1.0):
+        k = orc.row_k(C, sparsity)
+        Wd = W.clone().to(dev())
+        ops.wanda_row_select_apply(Wd, sd, k)  # no mask, no count: the bulk-copy kernel
+        Wref, _ = orc.wanda_prune_rows(f32(W), s, sparsity)
+        assert np.array_equal(f32(Wd).view(np.uint32), Wref.view(np.uint32)), (dt, C, sparsity)
+        # and the round-2 kernel (taken when a mask is requested) agrees bit for bit
+        Wm = W.clone().to(dev())
+        ops.wanda_row_select_apply(Wm, sd, k, mask_bits=ops.alloc_mask_bits(R, C, dev()))
+        assert torch.equal(Wd, Wm)
+
+
+@pytest.mark.parametrize("dt", ["fp16", "bf16"])
+def test_row_select_bulk_copy_kernel_ties_nonfinite_and_views(dt):
+    from ecoflap_b200 import ops
+
+    R, C = 64, 2048
+    W = synth_w(R, C, dt, seed=21)
+    W[:, 1024:] = W[:, :1024]
+    W[3] = 0
+    W[4, ::2] = 0
+    W[5] = W[5, 0]
+    W[6, 5] = float("inf")
+    W[7, :1500] = float("inf")
+    W[8, 100:1700] = float("nan")
+    s = np.full(C, 2.0, dtype=np.float32)
+    s[100:200] = 0.0
+    s[11] = 1e30
+    for sparsity in (0.5, 0.25, 0.75, 0.04):
+        k = orc.row_k(C, sparsity)
+        Wd = W.clone().to(dev())
+        ops.wanda_row_select_apply(Wd, torch.from_numpy(s).to(dev()), k)
+        _, mref = orc.wanda_prune_rows(f32(W), s, sparsity)
+        got, orig = Wd.cpu().view(torch.int16).numpy(), W.view(torch.int16).numpy()
+        assert np.array_equal(got[~mref], orig[~mref]) and not got[mref].any(), (dt, sparsity)
+    # all-zero norms: the first k columns of every row (finite weights: inf * 0 would be a NaN score that sorts last)
+    Wf = torch.nan_to_num(W, nan=0.5, posinf=1.0, neginf=-1.0)
+    Wd = Wf.clone().to(dev())
+    ops.wanda_row_select_apply(Wd, torch.zeros(C, device=dev()), 1000)
+    assert not Wd[:, :1000].any() and torch.equal(Wd[:, 1000:].cpu(), Wf[:, 1000:])
+    # a strided view (ld = 4096): the bulk copies must respect the leading dimension
+    big = synth_w(40, 4096, dt, seed=9).to(dev())
+    view, before = big[:, 1024:3072], big.clone()
+    sv = synth_norm(2048, seed=3)
+    ref, _ = orc.wanda_prune_rows(f32(view), sv, 0.5)
+    ops.wanda_row_select_apply(view, torch.from_numpy(sv).to(dev()), 1024)
+    assert np.array_equal(f32(view), ref)
+    assert torch.equal(big[:, :1024], before[:, :1024]) and torch.equal(big[:, 3072:], before[:, 3072:])
+
+
+def test_row_select_bulk_copy_kernel_batched_block():
+    """A T5 block in one call: CTAs cross matrix boundaries (different norms, different k) inside the bulk-copy kernel."""
+    from ecoflap_b200 import ops
+
+    shapes = [(2048, 2048), (517, 2048), (3, 2048), (1, 2048), (5120, 2048), (640, 5120), (2048, 5120)]
+    ks = [1024, 1064, 0, 2048, 613, 2560, 2662]
+    Ws = [synth_w(r, c, "bf16", seed=13 * i + c).to(dev()) for i, (r, c) in enumerate(shapes)]
+    ss = [torch.from_numpy(synth_norm(c, seed=i + c)).to(dev()) for i, (r, c) in enumerate(shapes)]
+    batched = [w.clone() for w in Ws]
+    ops.wanda_row_select_apply_batched([(w, s, k) for w, s, k in zip(batched, ss, ks)])
+    for i, (w, s, k) in enumerate(zip(Ws, ss, ks)):
+        one = w.clone()
+        ops.wanda_row_select_apply(one, s, k, mask_bits=ops.alloc_mask_bits(*shapes[i], dev()))  # round-2 kernel
+        assert torch.equal(one, batched[i]), shapes[i]
+        assert bool(((batched[i] == 0).sum(1) >= k).all())
+    ref, _ = orc.wanda_prune_rows(f32(Ws[1]), ss[1].cpu().numpy(), 1064 / 2048 + 1e-9)
+    assert np.array_equal(f32(batched[1]), ref)
+
+
+
 # ---------------------------------------------------------------------------- A6
 @pytest.mark.parametrize("dt", ["fp16", "bf16", "fp32"])
 @pytest.mark.parametrize("nm", [(2, 4), (4, 8), (1, 4), (3, 8), (2, 3), (5, 16), (1, 1)])
