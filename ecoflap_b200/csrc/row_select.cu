@@ -338,7 +338,8 @@ static int rs_check(const ecf_row_desc& d, int i) {
 // the bulk-copy kernel (row_select_tma.cuh): 16-bit weights, whole 256-column tiles, no mask / zero-count outputs
 static bool rs_tma_ok(const ecf_row_desc& d) {
   return d.dtype != ECF_F32 && (d.C == 768 || d.C == 1024 || d.C == 2048 || d.C == 3072 || d.C == 4096 || d.C == 5120) &&
-         (d.ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(d.W) & 15) == 0) && d.mask_bits == nullptr && d.n_zero == nullptr;
+         (d.ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(d.W) & 15) == 0) && ((reinterpret_cast<uintptr_t>(d.scaler_row) & 15) == 0) &&
+         d.mask_bits == nullptr && d.n_zero == nullptr;
 }
 
 static bool rs_fast_ok(const ecf_row_desc& d) {

@@ -38,8 +38,8 @@ constexpr int kRtBand = 32;    // stop narrowing once the bracket holds this man
 struct RtShared {
   uint64_t mbar[kRtWarps][2];
   unsigned long long thr[kRtWarps];
-  int cand_n[kRtWarps];
-  unsigned long long cand[kRtWarps][kRtCap];  // key << 32 | column
+  uint16_t cols[kRtWarps][kRtCap];
+  alignas(16) unsigned long long cand[kRtWarps][kRtCap + 2];  // key << 32 | column, or packed 32-bit candidates (+ padding)
 };
 
 __device__ __forceinline__ void rt_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -57,21 +57,25 @@ __device__ __forceinline__ float rt_q(const float* qs, uint32_t col) {
 }
 
 // Lane-local walk over this lane's bracket elements (bit e of `bm`: element ebase + e of the lane: vector e >> 3, slot e & 7).
-//   MODE 0: append (key, column) to the candidate list      MODE 1: count keys < a
-//   MODE 2: count keys == a with column < b                 MODE 3: zero the element in global memory when (key, column) <= thr
+//   MODE 5: write the column to slots b, b + 1, ... of `cols` (returns the next free slot)
+//   MODE 1: count keys < a          MODE 2: count keys == a with column < b
+//   MODE 3: zero the element in global memory when (key, column) <= thr
 template <int DT, int C, int MODE>
 __device__ __forceinline__ int rt_walk(uint32_t bm, int ebase, const unsigned char* buf, char* wrow, const float* qs, int lane, uint32_t a,
-                                       uint32_t b, unsigned long long thr, unsigned long long* cand, int* cand_n) {
+                                       uint32_t b, unsigned long long thr, unsigned long long* cand, uint16_t* cols) {
   int c = 0;
+  if constexpr (MODE == 5) {
+    if (bm == 0) return (int)b;
+  }
   while (bm) {
     const int e = ebase + __ffs((int)bm) - 1;
     bm &= bm - 1;
     const uint32_t col = (uint32_t)(((e >> 3) * 32 + lane) * 8 + (e & 7));
     const float w = load_elem<DT>(buf, col);
     const uint32_t key = score_key(wanda_score(w, rt_q<C>(qs, col)));
-    if constexpr (MODE == 0) {
-      const int slot = atomicAdd(cand_n, 1);
-      if (slot < kRtCap) cand[slot] = ((unsigned long long)key << 32) | col;
+    if constexpr (MODE == 5) {
+      cols[b + c] = (uint16_t)col;
+      ++c;
     } else if constexpr (MODE == 1) {
       c += key < a ? 1 : 0;
     } else if constexpr (MODE == 2) {
@@ -80,6 +84,7 @@ __device__ __forceinline__ int rt_walk(uint32_t bm, int ebase, const unsigned ch
       if ((((unsigned long long)key << 32) | col) <= thr) store_zero<DT>(wrow, col);
     }
   }
+  if constexpr (MODE == 5) return (int)b + c;
   return c;
 }
 
@@ -116,18 +121,34 @@ __global__ void __launch_bounds__(kRtWarps * 32, MINB) row_select_tma_kernel(con
     if (ra >= rb) continue;  // uniform over the CTA
     const int k = M.k;
     const int64_t ld = M.ld;
-    __syncthreads();  // every warp is done with the previous matrix' table
-    for (int c = tid; c < C; c += kRtWarps * 32)
-      qs[((c & 4) ? C / 2 : 0) + ((c >> 3) << 2) + (c & 3)] = __fadd_rn(sqrtf(M.s[c]), 0.f);
-    __syncthreads();
-
+    // the first row of every warp starts its trip now (its buffer is free: the previous matrix' last row ended with a
+    // __syncwarp); the table of sqrt(scaler_row) is built underneath that latency
     int r = ra + warp;
     char* wrow = reinterpret_cast<char*>(M.W) + (int64_t)r * ld * 2;
     const int64_t row_step = (int64_t)kRtWarps * ld * 2;
+    if (r < rb && lane == 0) rt_bulk_load(mybuf + stage * ROWB, wrow, ROWB, &sh.mbar[warp][stage]);
+    {
+      constexpr int QV = C / 4, QIT = (QV + kRtWarps * 32 - 1) / (kRtWarps * 32);
+      float4 s4[QIT];
+#pragma unroll
+      for (int it = 0; it < QIT; ++it) {  // all loads in flight before the first use
+        const int idx = tid + it * kRtWarps * 32;
+        s4[it] = idx < QV ? __ldg(reinterpret_cast<const float4*>(M.s) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      __syncthreads();  // every warp is done with the previous matrix' table
+#pragma unroll
+      for (int it = 0; it < QIT; ++it) {
+        const int idx = tid + it * kRtWarps * 32;  // columns 4 idx .. 4 idx + 3: half (idx & 1) of vector idx >> 1
+        if (idx < QV)
+          *reinterpret_cast<float4*>(qs + ((idx & 1) ? C / 2 : 0) + ((idx >> 1) << 2)) =
+              make_float4(__fadd_rn(sqrtf(s4[it].x), 0.f), __fadd_rn(sqrtf(s4[it].y), 0.f), __fadd_rn(sqrtf(s4[it].z), 0.f),
+                          __fadd_rn(sqrtf(s4[it].w), 0.f));
+      }
+      __syncthreads();
+    }
     bool carry = false;
     uint32_t t_prev = 0;
     float inv_rho = 1.f;  // coarse-key units per element near the threshold
-    if (r < rb && lane == 0) rt_bulk_load(mybuf + stage * ROWB, wrow, ROWB, &sh.mbar[warp][stage]);
 
     for (; r < rb; r += kRtWarps, wrow += row_step) {
       const bool has_next = r + kRtWarps < rb;
@@ -169,17 +190,20 @@ __global__ void __launch_bounds__(kRtWarps * 32, MINB) row_select_tma_kernel(con
           const uint32_t p = min(max(t_prev, 1u), kRfInf - 1u);
           const int c = warp_sum(rf_count1<NP>(co, p));
           if (c < k) { lo = p; c_lo = c; } else { hi = p; c_hi = c; }
-          // pass 2: two pivots at the keys the carried density predicts for ranks k -+ band/2
-          const float centre = (float)p + (float)(k - c) * inv_rho, half = (float)(kRtBand / 2) * inv_rho;
-          const int lo_lim = (int)lo + 1, hi_lim = (int)hi - 1;
-          if (lo_lim <= hi_lim) {
-            const int pl = min(max(__float2int_rd(centre - half), lo_lim), hi_lim);
-            const int ph = min(max(__float2int_ru(centre + half), lo_lim), hi_lim);
-            const int cc = warp_sum(rf_count2<NP>(co, (uint32_t)pl, (uint32_t)ph));
-            const int cl = cc & 0xffff, ch = cc >> 16;
-            if (cl >= k) { hi = (uint32_t)pl; c_hi = cl; }
-            else if (ch < k) { lo = (uint32_t)ph; c_lo = ch; }
-            else { lo = (uint32_t)pl; c_lo = cl; hi = (uint32_t)ph; c_hi = ch; }
+          // pass 2: one pivot at the key the carried density predicts for rank k + band/2 (k-th above p) or k - band/2
+          // (k-th below p): the bracket between the two pivots then holds |k - c| + band/2 elements
+          const float dist = ((float)abs(k - c) + (float)(kRtBand / 2)) * inv_rho;
+          const int step = max(__float2int_ru(dist), 1);
+          if (c < k) {
+            const uint32_t p2 = min(p + (uint32_t)step, kRfInf - 1u);
+            if (p2 > lo) {
+              const int c2 = warp_sum(rf_count1<NP>(co, p2));
+              if (c2 < k) { lo = p2; c_lo = c2; } else { hi = p2; c_hi = c2; }
+            }
+          } else if ((int)p - step >= 1) {
+            const uint32_t p2 = p - (uint32_t)step;
+            const int c2 = warp_sum(rf_count1<NP>(co, p2));
+            if (c2 < k) { lo = p2; c_lo = c2; } else { hi = p2; c_hi = c2; }
           }
         } else {
           // first row of this warp in this matrix: 32 samples, bitonic sort, two pivots around the sample quantile
@@ -261,31 +285,87 @@ __global__ void __launch_bounds__(kRtWarps * 32, MINB) row_select_tma_kernel(con
         }
       }
 
+      // The row buffer is free from here on (bracket elements are re-read from global memory: the vector stores above left
+      // them untouched and this warp's lines are L2 hits), so with one stage the next row's copy starts now and has the
+      // gather / ranking / patch of this row to land.
+      __syncwarp();  // every lane has read the buffer; also orders the vector stores before the scalar reads / patches below
+      if constexpr (STAGES == 1) {
+        if (has_next && lane == 0) rt_bulk_load(mybuf, wrow + row_step, ROWB, &sh.mbar[warp][0]);
+      }
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(wrow);
+
       // ---- exact ranking of the bracket by (fp32 key, column) ----
       const int m = c_hi - c_lo, need = k - c_lo;  // bracket size, how many of it must go (1 <= need <= m when m > 0)
       if (m > 0) {
         if (m <= kRtCap) {
-          if (lane == 0) sh.cand_n[warp] = 0;
-          __syncwarp();
+          // slots of this lane's candidates: exclusive prefix sum of the per-lane counts (no atomics)
+          int mine = 0;
 #pragma unroll
-          for (int i = 0; i < NBM; ++i)
-            rt_walk<DT, C, 0>(bm[i], 32 * i, buf, wrow, qs, lane, 0, 0, 0ull, sh.cand[warp], &sh.cand_n[warp]);
-          __syncwarp();  // also orders every lane's vector stores before the scalar patches below
-          unsigned long long thr = ~0ull;  // need == m: the whole bracket goes
-          if (need < m) {
-            for (int t = lane; t < m; t += 32) {
-              const unsigned long long me = sh.cand[warp][t];
-              int rank = 0;
-#pragma unroll 4
-              for (int j = 0; j < m; ++j) rank += sh.cand[warp][j] < me ? 1 : 0;
-              if (rank == need - 1) sh.thr[warp] = me;
-            }
-            __syncwarp();
-            thr = sh.thr[warp];
+          for (int i = 0; i < NBM; ++i) mine += __popc(bm[i]);
+          int incl = mine;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
           }
+          int slot = incl - mine;
+          // When the bracket spans at most 8 coarse keys below the clamp, (exact key - lo * 2^16) fits 19 bits and the column
+          // 13: a candidate is ONE 32-bit word and the ranking loop costs half.
+          const bool packed = hi - lo <= 8u && hi <= 0x7bffu;
+          unsigned long long* cand = sh.cand[warp];
+          uint32_t* cand32 = reinterpret_cast<uint32_t*>(cand);
+          // gather in two steps: the lanes first list the COLUMNS of their bracket elements (a short lane-local loop over
+          // set bits, as many trips as the fullest lane has candidates), then candidate t gets its exact key from lane
+          // t mod 32 -- one parallel step instead of one per trip
+          uint16_t* cols = sh.cols[warp];
+#pragma unroll
+          for (int i = 0; i < NBM; ++i) slot = rt_walk<DT, C, 5>(bm[i], 32 * i, src, wrow, qs, lane, 0, (uint32_t)slot, 0ull, cand, cols);
+          __syncwarp();
           for (int t = lane; t < m; t += 32) {
-            const unsigned long long me = sh.cand[warp][t];
-            if (me <= thr) store_zero<DT>(wrow, (uint32_t)me);
+            const uint32_t col = cols[t];
+            const uint32_t key = score_key(wanda_score(load_elem<DT>(src, col), rt_q<C>(qs, col)));
+            if (packed) cand32[t] = ((key - (lo << 16)) << 13) | col;
+            else cand[t] = ((unsigned long long)key << 32) | col;
+          }
+          if (packed && lane < 4) cand32[m + lane] = 0xffffffffu;  // padding up to a multiple of 4
+          __syncwarp();  // also orders every lane's vector stores before the scalar patches below
+          if (packed) {
+            uint32_t thr = 0xffffffffu;  // need == m: the whole bracket goes
+            if (need < m) {
+              for (int t = lane; t < m; t += 32) {
+                const uint32_t me = cand32[t];
+                int rank = 0;
+#pragma unroll 2
+                for (int j = 0; j < m; j += 4) {
+                  const uint4 o = *reinterpret_cast<const uint4*>(cand32 + j);
+                  rank += (o.x < me ? 1 : 0) + (o.y < me ? 1 : 0) + (o.z < me ? 1 : 0) + (o.w < me ? 1 : 0);
+                }
+                if (rank == need - 1) sh.thr[warp] = me;
+              }
+              __syncwarp();
+              thr = (uint32_t)sh.thr[warp];
+            }
+            for (int t = lane; t < m; t += 32) {
+              const uint32_t me = cand32[t];
+              if (me <= thr) store_zero<DT>(wrow, me & 0x1fffu);
+            }
+          } else {
+            unsigned long long thr = ~0ull;
+            if (need < m) {
+              for (int t = lane; t < m; t += 32) {
+                const unsigned long long me = cand[t];
+                int rank = 0;
+#pragma unroll 4
+                for (int j = 0; j < m; ++j) rank += cand[j] < me ? 1 : 0;
+                if (rank == need - 1) sh.thr[warp] = me;
+              }
+              __syncwarp();
+              thr = sh.thr[warp];
+            }
+            for (int t = lane; t < m; t += 32) {
+              const unsigned long long me = cand[t];
+              if (me <= thr) store_zero<DT>(wrow, (uint32_t)me);
+            }
           }
         } else {
           // heavy ties: the bracket is a single coarse value.  Bisect the fp32 key, then the column.
@@ -297,7 +377,7 @@ __global__ void __launch_bounds__(kRtWarps * 32, MINB) row_select_tma_kernel(con
               const uint32_t pv = L + ((H - L) >> 1);
               int c = 0;
 #pragma unroll
-              for (int i = 0; i < NBM; ++i) c += rt_walk<DT, C, 1>(bm[i], 32 * i, buf, wrow, qs, lane, pv, 0, 0ull, nullptr, nullptr);
+              for (int i = 0; i < NBM; ++i) c += rt_walk<DT, C, 1>(bm[i], 32 * i, src, wrow, qs, lane, pv, 0, 0ull, nullptr, nullptr);
               c = warp_sum(c);
               if (c < need) { L = pv; cL = c; } else { H = pv; }
             }
@@ -307,7 +387,7 @@ __global__ void __launch_bounds__(kRtWarps * 32, MINB) row_select_tma_kernel(con
               const uint32_t pc = (CL + CH) >> 1;
               int c = 0;
 #pragma unroll
-              for (int i = 0; i < NBM; ++i) c += rt_walk<DT, C, 2>(bm[i], 32 * i, buf, wrow, qs, lane, L, pc, 0ull, nullptr, nullptr);
+              for (int i = 0; i < NBM; ++i) c += rt_walk<DT, C, 2>(bm[i], 32 * i, src, wrow, qs, lane, L, pc, 0ull, nullptr, nullptr);
               c = warp_sum(c);
               if (c < need2) CL = pc; else CH = pc;
             }
@@ -315,15 +395,11 @@ __global__ void __launch_bounds__(kRtWarps * 32, MINB) row_select_tma_kernel(con
           }
           // scalar patch of this lane's own bracket elements (after its own vector stores: same-thread order)
 #pragma unroll
-          for (int i = 0; i < NBM; ++i) rt_walk<DT, C, 3>(bm[i], 32 * i, buf, wrow, qs, lane, 0, 0, thr, nullptr, nullptr);
+          for (int i = 0; i < NBM; ++i) rt_walk<DT, C, 3>(bm[i], 32 * i, src, wrow, qs, lane, 0, 0, thr, nullptr, nullptr);
         }
       }
-      __syncwarp();  // every lane is done with this row's buffer, candidate list and threshold slot
-      if constexpr (STAGES == 1) {
-        if (has_next && lane == 0) rt_bulk_load(mybuf, wrow + row_step, ROWB, &sh.mbar[warp][0]);
-      } else {
-        stage ^= 1;
-      }
+      __syncwarp();  // every lane is done with this row's candidate list and threshold slot
+      if constexpr (STAGES == 2) stage ^= 1;
     }
   }
 }
