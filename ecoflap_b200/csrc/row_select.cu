@@ -310,8 +310,8 @@ static int run_row_select(void* W, int64_t R, int64_t C, int64_t ld, const float
 int row_select_fast_f16(RfBatch&, int, bool, cudaStream_t);
 int row_select_fast_bf16(RfBatch&, int, bool, cudaStream_t);
 int row_select_fast_f32(RfBatch&, int, bool, cudaStream_t);
-int row_select_tma_f16(RfBatch&, int, cudaStream_t);
-int row_select_tma_bf16(RfBatch&, int, cudaStream_t);
+int row_select_tma_f16(RfBatch&, int, int, size_t, cudaStream_t);
+int row_select_tma_bf16(RfBatch&, int, int, size_t, cudaStream_t);
 
 // tuning / A-B switches (read once): ECF_RS_NVMAX = vectors per lane cap of the fast kernel (1..8),
 // ECF_RS_KEEP=0 makes 16-bit rows with > 4 vectors per lane re-read the weights in the apply pass (fewer registers),
@@ -342,6 +342,32 @@ static bool rs_tma_ok(const ecf_row_desc& d) {
          d.mask_bits == nullptr && d.n_zero == nullptr;
 }
 
+// Second stream + events for running two bulk-copy launches of one call side by side (fork / join on the caller's stream:
+// legal under stream capture, where it becomes two parallel branches of the graph).  Created on the first call that is NOT
+// being captured (stream creation is not allowed while a capture is open); until then the launches stay in order.
+struct RsAux {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool ok = false;
+};
+static RsAux* rs_aux(cudaStream_t s) {
+  static RsAux aux;
+  static bool tried = false;
+  if (!tried) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+    tried = true;
+    aux.ok = cudaStreamCreateWithFlags(&aux.stream, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&aux.fork, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&aux.join, cudaEventDisableTiming) == cudaSuccess;
+    if (!aux.ok) (void)cudaGetLastError();
+  }
+  return aux.ok ? &aux : nullptr;
+}
+
 static bool rs_fast_ok(const ecf_row_desc& d) {
   const int vec = d.dtype == ECF_F32 ? 4 : 8;
   return (d.C % 8 == 0) && (d.ld % vec == 0) && ((reinterpret_cast<uintptr_t>(d.W) & 15) == 0) && d.C <= 32768;
@@ -368,8 +394,14 @@ extern "C" int ecf_wanda_row_select_apply_batched(const ecf_row_desc* descs, int
   static const bool keep = rs_env("ECF_RS_KEEP", 1) != 0;
   static const int prefetch = rs_env("ECF_RS_PREFETCH", 0);
   static const int tma = rs_env("ECF_RS_TMA", 1);  // 0: round-2 kernels only; 1 / 2: bulk-copy kernel with that many stages (C <= 2048)
+  static const int corun_short = rs_env("ECF_RS_CORUN_SHORT", 3);  // CTAs per SM of the short-row kernel in a side-by-side pair
+  static const int corun_pad_kb = rs_env("ECF_RS_CORUN_PAD_KB", 76);
+  static const int corun = rs_env("ECF_RS_CORUN", 1);  // 1: a long-row and a short-row bulk-copy launch of one call share the SMs
   bool done[ECF_ROW_MAX_BATCH];
   for (int i = 0; i < n; ++i) done[i] = descs[i].R == 0;
+  RfBatch tma_groups[ECF_ROW_MAX_BATCH];
+  int tma_dtype[ECF_ROW_MAX_BATCH];
+  int n_tma = 0;
   for (int i = 0; i < n; ++i) {
     if (done[i]) continue;
     const ecf_row_desc& d0 = descs[i];
@@ -387,7 +419,7 @@ extern "C" int ecf_wanda_row_select_apply_batched(const ecf_row_desc* descs, int
     }
     // every remaining matrix with this row length and dtype (and the same kernel) joins the launch
     const bool use_tma = tma != 0 && rs_tma_ok(d0);
-    RfBatch tb;
+    RfBatch& tb = use_tma ? tma_groups[n_tma] : tma_groups[ECF_ROW_MAX_BATCH - 1];  // (the last slot doubles as scratch: n_tma < n)
     tb.n = 0;
     tb.C = (int)d0.C;
     tb.prefetch = prefetch;
@@ -400,9 +432,8 @@ extern "C" int ecf_wanda_row_select_apply_batched(const ecf_row_desc* descs, int
       M.batch_begin = 0;
       done[j] = true;
     }
-    if (use_tma) {
-      st = d0.dtype == ECF_F16 ? row_select_tma_f16(tb, tma, s) : row_select_tma_bf16(tb, tma, s);
-      if (st != ECF_OK) return st;
+    if (use_tma) {  // launched below, once every group of the call is known
+      tma_dtype[n_tma++] = d0.dtype;
       continue;
     }
     switch (d0.dtype) {
@@ -411,6 +442,27 @@ extern "C" int ecf_wanda_row_select_apply_batched(const ecf_row_desc* descs, int
       default: st = row_select_fast_bf16(tb, nv_max, keep, s); break;
     }
     if (st != ECF_OK) return st;
+  }
+  auto launch_tma = [&](int g, int share, size_t pad, cudaStream_t on) {
+    return tma_dtype[g] == ECF_F16 ? row_select_tma_f16(tma_groups[g], tma, share, pad, on) : row_select_tma_bf16(tma_groups[g], tma, share, pad, on);
+  };
+  // A T5 block is one launch of short rows (C = 2048: q, k, v, o, wi) and one of long rows (wo, C = 5120: only 2 048 rows, one
+  // per warp -- a latency-bound 17 us on its own).  Side by side the long-row kernel keeps ONE four-warp CTA per SM (its
+  // dynamic shared memory is padded so that a second one does not fit next to the others) and the short-row kernel three
+  // CTAs: 28 warps per SM in all, and the long rows' latency hides behind the short rows' work.
+  RsAux* aux = nullptr;
+  if (corun != 0 && n_tma == 2 && (tma_groups[0].C >= 3072) != (tma_groups[1].C >= 3072)) aux = rs_aux(s);
+  if (aux != nullptr) {
+    const int big = tma_groups[0].C >= 3072 ? 0 : 1;
+    ECF_CUDA_OK(cudaEventRecord(aux->fork, s));
+    ECF_CUDA_OK(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
+    if ((st = launch_tma(big, 1, (size_t)corun_pad_kb * 1024, aux->stream)) != ECF_OK) return st;
+    if ((st = launch_tma(1 - big, corun_short, 0, s)) != ECF_OK) return st;
+    ECF_CUDA_OK(cudaEventRecord(aux->join, aux->stream));
+    ECF_CUDA_OK(cudaStreamWaitEvent(s, aux->join, 0));
+  } else {
+    for (int g = 0; g < n_tma; ++g)
+      if ((st = launch_tma(g, 0, 0, s)) != ECF_OK) return st;
   }
   return ECF_OK;
 }

@@ -32,7 +32,7 @@ using umma::mbar_wait;
 using umma::smem_u32;
 
 constexpr int kRtWarps = 8;    // rows in flight per CTA
-constexpr int kRtCap = 128;    // exact-ranking capacity per row
+constexpr int kRtCap = 64;     // exact-ranking capacity per row (brackets end at <= 32 elements unless they are one coarse key)
 constexpr int kRtBand = 32;    // stop narrowing once the bracket holds this many elements
 
 struct RtShared {
@@ -88,8 +88,8 @@ __device__ __forceinline__ int rt_walk(uint32_t bm, int ebase, const unsigned ch
   return c;
 }
 
-template <int DT, int NV, int STAGES, int MINB>
-__global__ void __launch_bounds__(kRtWarps * 32, MINB) row_select_tma_kernel(const __grid_constant__ RfBatch tb) {
+template <int DT, int NV, int STAGES, int MINB, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, MINB) row_select_tma_kernel(const __grid_constant__ RfBatch tb) {
   constexpr int NP = 4 * NV;     // packed pairs per lane
   constexpr int C = NV * 256;    // row length
   constexpr uint32_t ROWB = C * 2;
@@ -125,20 +125,20 @@ __global__ void __launch_bounds__(kRtWarps * 32, MINB) row_select_tma_kernel(con
     // __syncwarp); the table of sqrt(scaler_row) is built underneath that latency
     int r = ra + warp;
     char* wrow = reinterpret_cast<char*>(M.W) + (int64_t)r * ld * 2;
-    const int64_t row_step = (int64_t)kRtWarps * ld * 2;
+    const int64_t row_step = (int64_t)WARPS * ld * 2;
     if (r < rb && lane == 0) rt_bulk_load(mybuf + stage * ROWB, wrow, ROWB, &sh.mbar[warp][stage]);
     {
-      constexpr int QV = C / 4, QIT = (QV + kRtWarps * 32 - 1) / (kRtWarps * 32);
+      constexpr int QV = C / 4, QIT = (QV + WARPS * 32 - 1) / (WARPS * 32);
       float4 s4[QIT];
 #pragma unroll
       for (int it = 0; it < QIT; ++it) {  // all loads in flight before the first use
-        const int idx = tid + it * kRtWarps * 32;
+        const int idx = tid + it * WARPS * 32;
         s4[it] = idx < QV ? __ldg(reinterpret_cast<const float4*>(M.s) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       __syncthreads();  // every warp is done with the previous matrix' table
 #pragma unroll
       for (int it = 0; it < QIT; ++it) {
-        const int idx = tid + it * kRtWarps * 32;  // columns 4 idx .. 4 idx + 3: half (idx & 1) of vector idx >> 1
+        const int idx = tid + it * WARPS * 32;  // columns 4 idx .. 4 idx + 3: half (idx & 1) of vector idx >> 1
         if (idx < QV)
           *reinterpret_cast<float4*>(qs + ((idx & 1) ? C / 2 : 0) + ((idx >> 1) << 2)) =
               make_float4(__fadd_rn(sqrtf(s4[it].x), 0.f), __fadd_rn(sqrtf(s4[it].y), 0.f), __fadd_rn(sqrtf(s4[it].z), 0.f),
@@ -150,8 +150,8 @@ __global__ void __launch_bounds__(kRtWarps * 32, MINB) row_select_tma_kernel(con
     uint32_t t_prev = 0;
     float inv_rho = 1.f;  // coarse-key units per element near the threshold
 
-    for (; r < rb; r += kRtWarps, wrow += row_step) {
-      const bool has_next = r + kRtWarps < rb;
+    for (; r < rb; r += WARPS, wrow += row_step) {
+      const bool has_next = r + WARPS < rb;
       if constexpr (STAGES == 2) {
         // the other buffer was last read before the __syncwarp that ended the previous row
         if (has_next && lane == 0) rt_bulk_load(mybuf + (stage ^ 1) * ROWB, wrow + row_step, ROWB, &sh.mbar[warp][stage ^ 1]);
@@ -405,18 +405,26 @@ __global__ void __launch_bounds__(kRtWarps * 32, MINB) row_select_tma_kernel(con
 }
 
 // ---------------------------------------------------------------------------------------------- host
-template <int DT, int NV, int STAGES, int MINB>
-static int rt_launch(RfBatch& tb, cudaStream_t stream) {
-  auto kern = row_select_tma_kernel<DT, NV, STAGES, MINB>;
-  const size_t smem = (size_t)NV * 256 * 4 + (size_t)kRtWarps * STAGES * NV * 512;
-  static bool opted = false;
-  if (!opted) {
+// share != 0: this launch runs NEXT TO another row-select launch on a second stream (row_select.cu).  The grid is then capped
+// at `share` CTAs per SM and the dynamic shared memory padded to `pad_smem`, so that the two kernels split every SM the same
+// way whichever is dispatched first.
+template <int DT, int NV, int STAGES, int MINB, int WARPS = kRtWarps>
+static int rt_launch(RfBatch& tb, int share, size_t pad_smem, cudaStream_t stream) {
+  static_assert(WARPS <= kRtWarps, "RtShared is sized for kRtWarps rows per CTA");
+  auto kern = row_select_tma_kernel<DT, NV, STAGES, MINB, WARPS>;
+  size_t smem = (size_t)NV * 256 * 4 + (size_t)WARPS * STAGES * NV * 512;
+  if (share != 0 && smem < pad_smem) smem = pad_smem;
+  static size_t opted = 0;
+  if (smem > opted) {
     ECF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    opted = true;
+    // the largest shared-memory carve-out whatever the launch needs: two kernels only share an SM when they agree on it
+    ECF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    opted = smem;
   }
   int occ = 0;
-  ECF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kRtWarps * 32, smem));
+  ECF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
   if (occ < 1) occ = 1;
+  if (share != 0 && occ > share) occ = share;
   int64_t rows = 0;
   for (int i = 0; i < tb.n; ++i) {
     tb.m[i].batch_begin = (int)rows;
@@ -424,25 +432,23 @@ static int rt_launch(RfBatch& tb, cudaStream_t stream) {
   }
   ECF_REQUIRE(rows < (1ll << 31), ECF_ERR_INVALID, "row_select: too many rows in one launch");
   tb.total_batches = (int)rows;
-  const int64_t want = (rows + kRtWarps - 1) / kRtWarps, cap = (int64_t)sm_count() * occ;
+  const int64_t want = (rows + WARPS - 1) / WARPS, cap = (int64_t)sm_count() * occ;
   const unsigned grid = (unsigned)(want < cap ? want : cap);
-  kern<<<grid, kRtWarps * 32, smem, stream>>>(tb);
+  kern<<<grid, WARPS * 32, smem, stream>>>(tb);
   ECF_CUDA_OK(cudaGetLastError());
   return ECF_OK;
 }
 
-// true when the round-3 kernel takes this row length
-inline bool rt_supported_c(int64_t C) { return C == 768 || C == 1024 || C == 2048 || C == 3072 || C == 4096 || C == 5120; }
-
 template <int DT>
-static int run_row_select_tma(RfBatch& tb, int stages, cudaStream_t stream) {
+static int run_row_select_tma(RfBatch& tb, int stages, int share, size_t pad_smem, cudaStream_t stream) {
   switch (tb.C) {
-    case 768: return stages == 2 ? rt_launch<DT, 3, 2, 4>(tb, stream) : rt_launch<DT, 3, 1, 4>(tb, stream);
-    case 1024: return stages == 2 ? rt_launch<DT, 4, 2, 4>(tb, stream) : rt_launch<DT, 4, 1, 4>(tb, stream);
-    case 2048: return stages == 2 ? rt_launch<DT, 8, 2, 3>(tb, stream) : rt_launch<DT, 8, 1, 4>(tb, stream);
-    case 3072: return rt_launch<DT, 12, 1, 2>(tb, stream);
-    case 4096: return rt_launch<DT, 16, 1, 2>(tb, stream);
-    case 5120: return rt_launch<DT, 20, 1, 2>(tb, stream);
+    case 768: return stages == 2 ? rt_launch<DT, 3, 2, 4>(tb, share, pad_smem, stream) : rt_launch<DT, 3, 1, 4>(tb, share, pad_smem, stream);
+    case 1024: return stages == 2 ? rt_launch<DT, 4, 2, 4>(tb, share, pad_smem, stream) : rt_launch<DT, 4, 1, 4>(tb, share, pad_smem, stream);
+    case 2048: return stages == 2 ? rt_launch<DT, 8, 2, 3>(tb, share, pad_smem, stream) : rt_launch<DT, 8, 1, 4>(tb, share, pad_smem, stream);
+    // long rows next to a short-row launch (share == 1): CTAs of four warps, one per SM, so that the short-row kernel keeps three
+    case 3072: return share == 1 ? rt_launch<DT, 12, 1, 4, 4>(tb, share, pad_smem, stream) : rt_launch<DT, 12, 1, 2>(tb, share, pad_smem, stream);
+    case 4096: return share == 1 ? rt_launch<DT, 16, 1, 4, 4>(tb, share, pad_smem, stream) : rt_launch<DT, 16, 1, 2>(tb, share, pad_smem, stream);
+    case 5120: return share == 1 ? rt_launch<DT, 20, 1, 4, 4>(tb, share, pad_smem, stream) : rt_launch<DT, 20, 1, 2>(tb, share, pad_smem, stream);
   }
   set_error("row_select: row length %d is not served by the bulk-copy kernel", tb.C);
   return ECF_ERR_INVALID;

@@ -2,5 +2,7 @@
 #include "row_select_tma.cuh"
 
 namespace ecf {
-int row_select_tma_f16(RfBatch& tb, int stages, cudaStream_t stream) { return run_row_select_tma<ECF_F16>(tb, stages, stream); }
+int row_select_tma_f16(RfBatch& tb, int stages, int share, size_t pad_smem, cudaStream_t stream) {
+  return run_row_select_tma<ECF_F16>(tb, stages, share, pad_smem, stream);
+}
 }  // namespace ecf

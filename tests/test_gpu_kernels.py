@@ -888,6 +888,25 @@ def test_prepare_hinv_vs_oracle_branches(variant):
         assert np.abs(np.diag(P) - np.diag(Pw)).max() <= 5e-2 * np.abs(np.diag(Pw)).max()
 
 
+def test_prepare_hinv_reversal_identity_equals_reference_order(monkeypatch):
+    """The one-factorisation prologue (U = (J chol(J H J) J)^-1) against the reference's three-step order on the same H,
+    and both against the fp64 factor: the shortcut must be at least as close to the exact U as the reference order."""
+    from ecoflap_b200 import accumulators
+
+    C = 1408
+    H = _spd_h(C, seed=11)
+    U64 = np.linalg.cholesky(np.linalg.inv(H.astype(np.float64))).T
+    monkeypatch.setattr(accumulators, "_REFERENCE_ORDER", False)
+    fast, _ = _prepare_hinv_gpu(H)
+    monkeypatch.setattr(accumulators, "_REFERENCE_ORDER", True)
+    ref, _ = _prepare_hinv_gpu(H)
+    assert np.all(np.tril(fast, -1) == 0) and np.all(np.diag(fast) > 0)
+    nrm = np.linalg.norm(U64)
+    e_fast, e_ref = np.linalg.norm(fast - U64) / nrm, np.linalg.norm(ref - U64) / nrm
+    assert np.linalg.norm(fast - ref) / np.linalg.norm(ref) < 1e-3  # the north_star Hessian tolerance
+    assert e_fast <= max(2.0 * e_ref, 1e-5), (e_fast, e_ref)
+
+
 def test_prepare_hinv_reference_golden_end_to_end():
     """fasterprune = prologue + block loop, product vs the reference's pruned weights (tests/golden/obs_prune.npz,
     incl. the dead-column case), H taken from the fixture so that only A9 + A10 are under test."""

@@ -1,4 +1,6 @@
-"""Batched per-row select of one FlanT5-XL block (encoder: q,k,v,o 2048x2048, wi_0/wi_1 5120x2048, wo 2048x5120)."""
+"""Batched per-row select of FlanT5-XL blocks (encoder: q,k,v,o 2048x2048, wi_0/wi_1 5120x2048, wo 2048x5120; decoder: the same
+plus the cross-attention q,k,v,o).  NB blocks with their own weights are captured back to back in one graph, so that one event
+pair spans ~0.3 ms (the event clock ticks in ~2 us steps on this box) and the graph-launch gap is amortised."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -7,32 +9,47 @@ from ecoflap_b200 import ops
 dev = torch.device("cuda", 0)
 PEAK = 6532.5
 torch.manual_seed(0)
-shapes = [(2048, 2048)] * 4 + [(5120, 2048)] * 2 + [(2048, 5120)]
-W0 = [(torch.randn(r, c, device=dev) * 0.02).bfloat16() for r, c in shapes]
-ss = [torch.rand(c, device=dev) + 0.1 for r, c in shapes]
-Ws = [w.clone() for w in W0]
-items = [(w, s, w.shape[1] // 2) for w, s in zip(Ws, ss)]
-flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-if len(sys.argv) > 1:  # ncu target: a few plain launches
-    for _ in range(2):
+ENC = [(2048, 2048)] * 4 + [(5120, 2048)] * 2 + [(2048, 5120)]
+DEC = [(2048, 2048)] * 8 + [(5120, 2048)] * 2 + [(2048, 5120)]
+which = os.environ.get("RS_BLOCKS", "enc,enc,enc,dec,dec,dec").split(",")
+blocks = []
+for b in which:
+    shapes = ENC if b == "enc" else DEC
+    W0 = [(torch.randn(r, c, device=dev) * 0.02).bfloat16() for r, c in shapes]
+    ss = [torch.rand(c, device=dev) + 0.1 for r, c in shapes]
+    Ws = [w.clone() for w in W0]
+    blocks.append((shapes, W0, Ws, [(w, s, w.shape[1] // 2) for w, s in zip(Ws, ss)]))
+flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+
+def restore():
+    for _, W0, Ws, _ in blocks:
         for w, w0 in zip(Ws, W0):
             w.copy_(w0)
-        flush.zero_()
+
+
+def run():
+    for _, _, _, items in blocks:
         ops.wanda_row_select_apply_batched(items)
+
+
+if len(sys.argv) > 1:  # ncu target: a few plain launches
+    for _ in range(2):
+        restore(); flush.zero_(); run()
     torch.cuda.synchronize()
     sys.exit(0)
-ops.wanda_row_select_apply_batched(items)
+run()
 torch.cuda.synchronize()
 g = torch.cuda.CUDAGraph()
+restore()
 with torch.cuda.graph(g):
-    ops.wanda_row_select_apply_batched(items)
+    run()
 ts = []
 for _ in range(10):
-    for w, w0 in zip(Ws, W0):
-        w.copy_(w0)
-    flush.zero_()
+    restore(); flush.zero_(); flush.sum()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); g.replay(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
 ms = sorted(ts)[len(ts) // 2]
-nbytes = sum(2 * r * c * 2 + 4 * c for r, c in shapes)
-print(f"t5 encoder block row select: {ms*1e3:.1f} us, {nbytes/ms/1e6:.0f} GB/s ({nbytes/ms/1e6/PEAK:.2f} of peak), {nbytes/1e6:.0f} MB")
+nbytes = sum(2 * r * c * 2 + 4 * c for shapes, _, _, _ in blocks for r, c in shapes)
+print(f"{len(blocks)} T5 blocks ({','.join(which)}) row select: {ms*1e3/len(blocks):.1f} us per block, {nbytes/ms/1e6:.0f} GB/s "
+      f"({nbytes/ms/1e6/PEAK:.3f} of peak), {nbytes/1e6:.0f} MB, min {min(ts)*1e3/len(blocks):.1f} max {max(ts)*1e3/len(blocks):.1f}")
