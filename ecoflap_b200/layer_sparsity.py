@@ -31,23 +31,175 @@ class _UniformSparsity:
         return self.ratio
 
 
+def _map_struct(x, fn):
+    if torch.is_tensor(x):
+        return fn(x)
+    if isinstance(x, (list, tuple)):
+        return type(x)(_map_struct(v, fn) for v in x)
+    if isinstance(x, dict):
+        return {k: _map_struct(v, fn) for k, v in x.items()}
+    return x
+
+
+def _copy_struct(dst, src):
+    if torch.is_tensor(dst):
+        dst.copy_(src)
+    elif isinstance(dst, (list, tuple)):
+        for d, s_ in zip(dst, src):
+            _copy_struct(d, s_)
+    elif isinstance(dst, dict):
+        for k in dst:
+            _copy_struct(dst[k], src[k])
+
+
 class _ReplayedLoss:
     """The zeroth-order loop evaluates the SAME no-grad forward 2 * #layers times per first-stage batch (588 layers x 4
     batches x 2 for BLIP-2); in eager mode each of those forwards is ~2 000 kernel launches issued by Python, and the GPU
-    idles behind the host.  The first evaluation of a batch is therefore captured in a CUDA graph (after two warm-up runs
+    idles behind the host.  The first evaluation of a batch is therefore captured in a CUDA graph (after a warm-up run
     on a side stream) and every later one is a replay: the same kernels on the same -- in place perturbed -- parameters,
     hence the same losses, without the launch overhead.  The batch is moved to the device once, before the capture (a
     pageable host-to-device copy cannot be captured).  Anything that cannot be captured (a model that synchronises or
     allocates on the host inside its forward) makes this wrapper fall back to calling ``loss_func`` directly for the rest
-    of the run.  ECF_ZO_GRAPH=0 switches it off."""
+    of the run.  ECF_ZO_GRAPH=0 switches it off.
 
-    def __init__(self, loss_func, model, device):
+    **Prefix cache** (ECF_ZO_PREFIX=0 switches it off).  Perturbing a layer of block b leaves the outputs of every block
+    that runs before b untouched, yet the plain loop recomputes them 2 * #layers times -- for BLIP-2 the 39 ViT-g blocks
+    (2 056 tokens per batch) are ~80 % of a forward and 336 of the 588 layers sit behind them in the T5.  The blocks
+    (children of an ``nn.ModuleList`` that hold a scored parameter) are put in execution order by the warm-up run; a graph
+    VARIANT with cut c returns the cached output of the blocks before c (their ``forward`` is replaced while the variant is
+    captured) and recomputes the rest, and every variant copies the outputs of the boundary blocks (c - 1 for every cut
+    c, and the last block of every ModuleList) into the cache as part of the graph.  ``dirty_from`` tracks, per batch, the
+    first block whose cached output does not correspond to the current weights: after an evaluation for a layer of block b
+    the blocks before b were recomputed with clean weights (their caches are fresh) and everything from b on is dirty, so
+    the next evaluation may cut at the largest cut <= min(b', dirty_from).  The cached tensors are what the full forward
+    would compute at that moment (same kernels, same inputs, including the rounding residue the earlier layers carry after
+    their +1 / -2 / +1 cycle), so losses and ratios are bit-identical to the uncached loop."""
+
+    last = None  # the most recent instance (tests read its statistics)
+
+    def __init__(self, loss_func, model, device, names=None):
         import os
 
         self.loss_func, self.model, self.device = loss_func, model, device
         self.enabled = (os.environ.get("ECF_ZO_GRAPH", "1") != "0" and torch.cuda.is_available()
                         and torch.device(device).type == "cuda")
         self._graphs = {}
+        self._batches = {}      # id(batch) -> (device batch, host batch kept alive)
+        self._pool = None
+        # prefix cache
+        self.prefix = self.enabled and os.environ.get("ECF_ZO_PREFIX", "1") != "0" and names is not None
+        self._stride = max(1, int(os.environ.get("ECF_ZO_PREFIX_STRIDE", "4")))
+        self._blocks = None     # block modules in execution order
+        self._block_of = {}     # parameter name -> index into _blocks
+        self._cuts = [0]
+        self._boundary = set()  # block indices whose output is cached
+        self._ret = {}          # cut -> {skipped block index: boundary block index whose cache it returns}
+        self._cache = {}        # id(batch) -> {boundary block index: cached output}
+        self._dirty = {}        # id(batch) -> first block whose cache is not valid for the current weights
+        self._own = set()       # blocks that keep their own (never refreshed) output as a structural stand-in
+        self.stats = {"replays": 0, "cuts_used": set(), "captures": 0}
+        _ReplayedLoss.last = self  # (tests look at the statistics of the most recent run)
+        if self.prefix:
+            self._find_blocks(names)
+
+    # -- prefix cache: structure ------------------------------------------------------------------------------------
+    def _find_blocks(self, names):
+        import torch.nn as nn
+
+        mods = dict(self.model.named_modules())
+        cand, owner = [], {}
+        for name in names:
+            parts = name.split(".")
+            blk = None
+            for j in range(1, len(parts)):  # OUTERMOST ancestor that is a child of a ModuleList (a T5Block, not its sub-layers)
+                parent = mods.get(".".join(parts[:j - 1])) if j > 1 else self.model
+                me = mods.get(".".join(parts[:j]))
+                if isinstance(parent, nn.ModuleList) and me is not None:
+                    blk = me
+                    break
+            if blk is not None:
+                owner[name] = blk
+                if all(blk is not c for c in cand):
+                    cand.append(blk)
+        if len(cand) < 2:
+            self.prefix = False
+            return
+        self._cand, self._owner = cand, owner
+
+    def _order_blocks(self, dev_batch):
+        """One eager forward with pre-hooks on the candidate blocks: execution order; every block must run exactly once."""
+        import torch.nn as nn
+
+        order, handles = [], []
+        for blk in self._cand:
+            handles.append(blk.register_forward_pre_hook(lambda m, a, _o=order: _o.append(m)))
+        try:
+            with torch.no_grad():
+                self.loss_func(self.model, dev_batch, True)
+        finally:
+            for h in handles:
+                h.remove()
+        if len(order) != len(self._cand) or len({id(m) for m in order}) != len(order):
+            self.prefix = False
+            return
+        self._blocks = order
+        index = {id(m): i for i, m in enumerate(order)}
+        self._block_of = {n: index[id(b)] for n, b in self._owner.items()}
+        # towers: maximal runs of consecutive blocks that share their parent ModuleList
+        parent_of = {}
+        for mod in self.model.modules():
+            if isinstance(mod, nn.ModuleList):
+                for ch in mod:
+                    parent_of[id(ch)] = id(mod)
+        towers, start = [], 0
+        for i in range(1, len(order) + 1):
+            if i == len(order) or parent_of.get(id(order[i])) != parent_of.get(id(order[start])):
+                towers.append((start, i - 1))
+                start = i
+        cuts = {0}
+        for t0, t1 in towers:
+            cuts.update(range(t0, t1 + 1, self._stride))
+        self._cuts = sorted(cuts)
+        self._boundary = {c - 1 for c in self._cuts if c > 0} | {t1 for _, t1 in towers}
+        for c in self._cuts:
+            ret = {}
+            for t0, t1 in towers:
+                last = t1 if t1 < c else (c - 1 if t0 < c else None)
+                if last is None:
+                    continue
+                # a skipped block answers with the boundary block's cache when both are the same kind of module (same output
+                # structure; its value only feeds the next skipped block), else with its own first output
+                ret.update({j: (last if type(order[j]) is type(order[last]) else j) for j in range(t0, last + 1)})
+            self._ret[c] = ret
+        self._own = {j for ret in self._ret.values() for j, src in ret.items() if src == j} - self._boundary
+
+    # -- running one variant ----------------------------------------------------------------------------------------
+    def _run(self, key, cut, dev_batch):
+        """loss_func with the blocks before `cut` answering from the cache and the boundary blocks from `cut` on writing to it"""
+        cache = self._cache.setdefault(key, {})
+        patched, handles = [], []
+        try:
+            if self.prefix and self._blocks is not None:
+                for j, src in self._ret[cut].items():
+                    blk = self._blocks[j]
+                    blk.forward = (lambda *a, _c=cache[src], **k: _c)
+                    patched.append(blk)
+                for j in self._boundary | self._own:
+                    if j in self._ret[cut]:
+                        continue
+
+                    def hook(mod, inp, out, _j=j, _update=j in self._boundary):
+                        if _j not in cache:
+                            cache[_j] = _map_struct(out, lambda t: t.detach().clone())
+                        elif _update:
+                            _copy_struct(cache[_j], out)
+                    handles.append(self._blocks[j].register_forward_hook(hook))
+            return self.loss_func(self.model, dev_batch, True)
+        finally:
+            for blk in patched:
+                del blk.forward
+            for h in handles:
+                h.remove()
 
     @staticmethod
     def _to_device(x, device):
@@ -59,43 +211,63 @@ class _ReplayedLoss:
             return type(x)(_ReplayedLoss._to_device(v, device) for v in x)
         return x
 
-    def __call__(self, batch):
-        """-> (loss as a fresh 0-d tensor, batch_len)"""
+    def _eager(self, batch):
+        with torch.no_grad():
+            return self.loss_func(self.model, batch, self.device != "cpu")
+
+    def __call__(self, batch, name=None):
+        """-> (loss as a fresh 0-d tensor, batch_len).  ``name``: the parameter that is perturbed right now (prefix cache)."""
         if not self.enabled:
-            with torch.no_grad():
-                return self.loss_func(self.model, batch, self.device != "cpu")
-        entry = self._graphs.get(id(batch))
-        if entry is None and len(self._graphs) >= 64:
+            return self._eager(batch)
+        key = id(batch)
+        if key not in self._batches and len(self._batches) >= 64:
             # a loader that builds new batch objects on every pass never hits the cache: stop capturing
             print("[ecoflap_b200] zeroth-order loader yields fresh batch objects on every pass; running eagerly")
             self.enabled = False
             self._graphs.clear()
-            with torch.no_grad():
-                return self.loss_func(self.model, batch, self.device != "cpu")
-        if entry is None:
-            try:
+            return self._eager(batch)
+        try:
+            if key not in self._batches:
                 dev_batch = self._to_device(batch, self.device)
                 side = torch.cuda.Stream(device=self.device)
                 side.wait_stream(torch.cuda.current_stream(self.device))
                 with torch.cuda.stream(side), torch.no_grad():
-                    for _ in range(2):
-                        self.loss_func(self.model, dev_batch, True)
+                    if self.prefix and self._blocks is None:
+                        self._order_blocks(dev_batch)
+                    self._run(key, 0, dev_batch)  # warm-up; fills the caches of a new batch
                 torch.cuda.current_stream(self.device).wait_stream(side)
                 torch.cuda.synchronize(self.device)
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph), torch.no_grad():
-                    loss, batch_len = self.loss_func(self.model, dev_batch, True)
-                entry = (graph, loss, int(batch_len), dev_batch, batch)  # (the batch is kept alive: ids are the keys)
-                self._graphs[id(batch)] = entry
-            except Exception as exc:  # not capturable: say so once, continue eagerly
-                print(f"[ecoflap_b200] zeroth-order forward not captured in a CUDA graph ({type(exc).__name__}: {exc}); running eagerly")
+                self._batches[key] = (dev_batch, batch)  # (the host batch is kept alive: ids are the keys)
+                self._dirty[key] = 0
+            dev_batch = self._batches[key][0]
+            cut = 0
+            blk = self._block_of.get(name) if (self.prefix and self._blocks is not None) else None
+            if blk is not None:
+                lim = min(blk, self._dirty[key])
+                cut = max(c for c in self._cuts if c <= lim)
+            entry = self._graphs.get((key, cut))
+            if entry is None:
+                if self._pool is None:
+                    self._pool = torch.cuda.graph_pool_handle()
                 torch.cuda.synchronize(self.device)
-                self.enabled = False
-                self._graphs.clear()
-                with torch.no_grad():
-                    return self.loss_func(self.model, batch, self.device != "cpu")
-        graph, loss, batch_len = entry[0], entry[1], entry[2]
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, pool=self._pool), torch.no_grad():
+                    loss, batch_len = self._run(key, cut, dev_batch)
+                entry = (graph, loss, int(batch_len))
+                self._graphs[(key, cut)] = entry
+                self.stats["captures"] += 1
+        except Exception as exc:  # not capturable: say so once, continue eagerly
+            print(f"[ecoflap_b200] zeroth-order forward not captured in a CUDA graph ({type(exc).__name__}: {exc}); running eagerly")
+            torch.cuda.synchronize(self.device)
+            self.enabled = False
+            self._graphs.clear()
+            return self._eager(batch)
+        graph, loss, batch_len = entry
         graph.replay()
+        self.stats["replays"] += 1
+        self.stats["cuts_used"].add(cut)
+        # blocks in [cut, blk) were recomputed with the current weights: their caches are fresh; from blk on they are not
+        self._dirty[key] = blk if blk is not None else 0
         return loss.clone(), batch_len
 
 
@@ -309,7 +481,7 @@ class LayerSparsity:
         device = next(iter(model.parameters())).device
         eps = self.noise_eps
         ghat = {k: 0.0 for k in names}
-        evaluate = _ReplayedLoss(loss_func, model, device)
+        evaluate = _ReplayedLoss(loss_func, model, device, names)
         for i, (name, param) in enumerate(zip(names, params)):
             print(i, name)
             seen = 0
@@ -322,9 +494,9 @@ class LayerSparsity:
                         break
                     seed = np.random.randint(1000000000)
                     self.zo_perturb_parameters([param], random_seed=seed, scaling_factor=1, zo_eps=eps)
-                    loss_plus, batch_len = evaluate(batch)
+                    loss_plus, batch_len = evaluate(batch, name)
                     self.zo_perturb_parameters([param], random_seed=seed, scaling_factor=-2, zo_eps=eps)
-                    loss_minus, batch_len = evaluate(batch)
+                    loss_minus, batch_len = evaluate(batch, name)
                     # restore (inexact in fp16/bf16 exactly as in the reference)
                     self.zo_perturb_parameters([param], random_seed=seed, scaling_factor=1, zo_eps=eps)
                     seen += batch_len
@@ -365,7 +537,7 @@ class LayerSparsity:
             batch_lens.append(int(batch_len))
             seen += int(batch_len)
         draws = edist.zo_draws_per_layer(batch_lens, self.num_samples, self.num_noise)
-        evaluate = _ReplayedLoss(loss_func, model, device)
+        evaluate = _ReplayedLoss(loss_func, model, device, names)
         seeds = [[int(np.random.randint(1000000000)) for _ in range(draws)] for _ in names]  # the reference's stream
         ghat_vec = torch.zeros(len(names), dtype=torch.float64, device=device)
         mismatch = False
@@ -384,9 +556,9 @@ class LayerSparsity:
                     seed = seeds[i][d]
                     d += 1
                     self.zo_perturb_parameters([param], random_seed=seed, scaling_factor=1, zo_eps=eps)
-                    loss_plus, batch_len = evaluate(batch)
+                    loss_plus, batch_len = evaluate(batch, name)
                     self.zo_perturb_parameters([param], random_seed=seed, scaling_factor=-2, zo_eps=eps)
-                    loss_minus, batch_len = evaluate(batch)
+                    loss_minus, batch_len = evaluate(batch, name)
                     self.zo_perturb_parameters([param], random_seed=seed, scaling_factor=1, zo_eps=eps)
                     seen += batch_len
                     acc += abs(((loss_plus - loss_minus) / (2 * eps)).item())

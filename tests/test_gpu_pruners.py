@@ -244,6 +244,26 @@ def test_zeroth_order_loop_matches_reference_on_its_cpu_noise_stream(method):
     np.testing.assert_allclose(np.array([sd[k] for k in keys]), g[f"{method}__res"], rtol=0, atol=2e-2, err_msg=method)
 
 
+@pytest.mark.parametrize("stride", ["1", "2"])
+def test_zeroth_order_prefix_cache_is_bit_identical_to_the_full_forward(monkeypatch, stride):
+    """The graph-replayed loop with cached block prefixes (_ReplayedLoss, cuts every `stride` blocks) against the same
+    loop with full forwards (ECF_ZO_PREFIX=0) and against eager forwards (ECF_ZO_GRAPH=0): identical g-hat sums and
+    ratios, bit for bit -- the cached outputs are what the full forward computes at that point of the loop."""
+    monkeypatch.setenv("ECF_ZO_PREFIX", "1")
+    monkeypatch.setenv("ECF_ZO_PREFIX_STRIDE", stride)
+    sums_c, sd_c = _stage1_product("MEZO-GradOnly_sum", noise_device="cpu")
+    from ecoflap_b200.layer_sparsity import _ReplayedLoss
+    st = _ReplayedLoss.last
+    assert st.enabled and st.prefix and st.stats["replays"] > 0, "the prefix-cached graph path must have run (no eager fallback)"
+    assert len(st.stats["cuts_used"]) >= 3 and max(st.stats["cuts_used"]) > 0, st.stats  # several prefixes were skipped
+    monkeypatch.setenv("ECF_ZO_PREFIX", "0")
+    sums_f, sd_f = _stage1_product("MEZO-GradOnly_sum", noise_device="cpu")
+    monkeypatch.setenv("ECF_ZO_GRAPH", "0")
+    sums_e, sd_e = _stage1_product("MEZO-GradOnly_sum", noise_device="cpu")
+    assert sums_c == sums_f == sums_e
+    assert sd_c == sd_f == sd_e
+
+
 # ------------------------------------------------------------------------------------------------ UPop / LLaMA entry points
 @pytest.mark.parametrize("gran", [None, "block"])
 def test_upop_blipbert_matches_reference(gran):
