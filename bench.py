@@ -275,6 +275,9 @@ def prune_wall(which=("wanda", "ecoflap"), verbose=False):
     dev = torch.device("cuda", local)
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
+    if world > 1:  # the communicator (and its peer mappings) is set up by the first collective: not part of prune()
+        dist.all_reduce(torch.zeros(1, device=dev))
+        torch.cuda.synchronize()
     out = {}
     for name in which:
         torch.manual_seed(0)
