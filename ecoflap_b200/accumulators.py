@@ -282,7 +282,9 @@ class SparseGPT:
         ops.obs_prune(W, Hinv, kth, blocksize, prune_n, prune_m)
         if isinstance(self.layer, _Conv1D):
             W = W.t()
-        self.layer.weight.data = W.reshape(self.layer.weight.shape).to(self.layer.weight.data.dtype)
+        # in place (the reference rebinds .data, sparsegpt_pruner.py:214): same values, but the storage the block's captured
+        # forward graph reads (pruners/sweep.py, _BlockReplay) stays the one that holds the pruned weights
+        self.layer.weight.data.copy_(W.reshape(self.layer.weight.shape))
 
     def free(self):
         # the reference also calls torch.cuda.empty_cache() here (sparsegpt_pruner.py:220-222): 588 cudaFree / cudaMalloc

@@ -135,6 +135,172 @@ def _run_block(layer, inp, cache, spec):
     return out
 
 
+class _BlockReplay:
+    """N2 -- the stage-2 block forward (wanda_pruner.py:250-253,281-285,530-533,560-563; sparsegpt_pruner.py:355-358,392-395).
+
+    The reference calls every block 2 x n_batches times from Python; with the LAVIS SparseGPT recipe (batch size 1) that is
+    256 eager forwards per block and the GPU idles behind the host.  Here G consecutive calibration batches form a group:
+    the G block forwards of a group are captured ONCE per block in a CUDA graph over static input / kwarg / output buffers
+    and every group of both passes is a replay (the weights are pruned in place between the passes, so the same graph
+    serves the second pass).  The kernels of a sample are the ones the eager call launches on the same data: the block
+    outputs are bit-identical to the eager sweep.  While the graph is captured the Linear hooks copy their input into a
+    staging buffer per DISTINCT input tensor (q / k / v hooks see one tensor and share one buffer, so the accumulators' own
+    de-duplication keeps working); after every replay of the first pass the group's staged inputs are copied to a buffer
+    that holds the hook inputs of ALL samples (the eager sweep keeps them alive as well, for its deferred launches), and at
+    the end of the pass ``add_batch`` is called per sample and Linear in the eager order -- the accumulators see the same
+    calls on the same data, so norms and Hessians are bit-identical too.  Anything irregular -- ragged shapes, per-sample kwargs that are not
+    tensors of one shape, a block adapter (CLIP), a forward that cannot be captured -- keeps the eager path.
+    ECF_BLOCK_GRAPH=0 switches it off, ECF_BLOCK_GRAPH_GROUP sets G (default 16)."""
+
+    last_stats = None
+    _keep = None  # (memory pool handle, the most recent graph: keeps the pool alive between blocks)
+
+    def __init__(self, layer, spec, autocast, subset, permute_names, group, n_groups):
+        self.layer, self.spec, self.autocast, self.subset = layer, spec, autocast, subset
+        self.permute_names = permute_names
+        self.G, self.n_groups = group, n_groups
+        self.full = []       # per distinct hook input: [n_groups * G, *x.shape], the first pass' inputs of every sample
+        self.filled = 0
+        self.graph = None
+        self.sin = self.sout = None
+        self.scache = {}     # kwarg name -> [G, ...] staging of per-sample tensors
+        self.shared = {}     # kwarg name -> the value every sample shares
+        self.stage = []      # per distinct hook input: [G, *x.shape]
+        self.stage_of = {}   # Linear name -> index into stage
+        self.failed = False
+        self.stats = {"captures": 0, "replays": 0}
+        _BlockReplay.last_stats = self.stats
+
+    @staticmethod
+    def eligible(inps, caches, batches, spec, group):
+        # a graph costs about as much host time to capture as its G forwards cost eagerly: it pays off from the fourth
+        # replay on (two groups x two passes) -- the batch-size-1 recipes; 16 batches of 8 stay eager
+        if os.environ.get("ECF_BLOCK_GRAPH", "1") == "0" or spec.block_adapter is not None or group < 2 or len(batches) < 2 * group \
+                or len(batches) % group != 0:
+            return False
+        x0 = inps[batches[0]]
+        if not (torch.is_tensor(x0) and x0.is_cuda):
+            return False
+        for j in batches:
+            x = inps[j]
+            if not torch.is_tensor(x) or x.shape != x0.shape or x.dtype != x0.dtype or x.device != x0.device:
+                return False
+            if caches[j].keys() != caches[batches[0]].keys():
+                return False
+        for k, v0 in caches[batches[0]].items():
+            for j in batches:
+                v = caches[j][k]
+                if torch.is_tensor(v0):
+                    if not torch.is_tensor(v) or v.shape != v0.shape or v.dtype != v0.dtype or v.device != v0.device:
+                        return False
+                elif v is not v0 and v != v0:
+                    return False
+        return True
+
+    def _kwargs(self, g):
+        kw = dict(self.shared)
+        for k, buf in self.scache.items():
+            kw[k] = buf[g]
+        return kw
+
+    def _capture(self, inps, caches, chunk):
+        G, c0 = self.G, caches[chunk[0]]
+        with torch.no_grad(), self.autocast():  # warm-up: lazy initialisations, and the shape of the block's output
+            out0 = _run_block(self.layer, inps[chunk[0]], c0, self.spec)
+        x0 = inps[chunk[0]]
+        self.sin = torch.empty((G,) + tuple(x0.shape), dtype=x0.dtype, device=x0.device)
+        self.sout = torch.empty((G,) + tuple(out0.shape), dtype=out0.dtype, device=out0.device)
+        del out0
+        for k, v in c0.items():
+            # a tensor that every sample shares (same object) stays a plain argument; per-sample tensors are staged
+            if torch.is_tensor(v) and any(caches[j][k] is not v for j in chunk):
+                self.scache[k] = torch.empty((G,) + tuple(v.shape), dtype=v.dtype, device=v.device)
+            else:
+                self.shared[k] = v
+        slot = {"g": 0, "seen": {}}
+
+        def make_stage_hook(name):
+            permute = name in self.permute_names
+
+            def hook(_, inp, out):
+                x = inp[0].detach()
+                if permute:
+                    x = x.permute(1, 0, 2)
+                key = (x.data_ptr(), tuple(x.shape), tuple(x.stride()), x.dtype)
+                # (the tensor itself is kept until the sample's forward ends: a freed activation's address may be handed
+                # to a later, different activation of the same shape, which would then pass for a shared input)
+                idx = slot["seen"].get(key, (None, None))[0]
+                if idx is None:
+                    if slot["g"] == 0:
+                        idx = len(self.stage)
+                        self.stage.append(torch.empty((G,) + tuple(x.shape), dtype=x.dtype, device=x.device))
+                        slot.setdefault("order", []).append(name)
+                    else:  # the same hook opened this distinct input in slot 0
+                        idx = self.stage_of[name]
+                    slot["seen"][key] = (idx, x)
+                    self.stage[idx][slot["g"]].copy_(x)
+                if slot["g"] == 0:
+                    self.stage_of[name] = idx
+                elif self.stage_of.get(name) != idx:
+                    raise RuntimeError("hook inputs are shared differently from sample to sample")
+            return hook
+
+        handles = [self.subset[name].register_forward_hook(make_stage_hook(name)) for name in self.subset]
+        try:
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            # One memory pool for the graphs of all blocks: a private pool per block costs a cudaMalloc / cudaFree round trip
+            # of hundreds of MB per block (measured: the BLIP-2 run got slower than the eager sweep).  A pool dies with the last
+            # graph that uses it, so the previous block's graph is kept until this one exists.
+            if _BlockReplay._keep is None:
+                _BlockReplay._keep = (torch.cuda.graph_pool_handle(), None)
+            with torch.cuda.graph(graph, pool=_BlockReplay._keep[0]), torch.no_grad(), self.autocast():
+                for g in range(G):
+                    slot["g"], slot["seen"] = g, {}
+                    self.sout[g].copy_(_run_block(self.layer, self.sin[g], self._kwargs(g), self.spec))
+        finally:
+            for h in handles:
+                h.remove()
+        self.graph = graph
+        _BlockReplay._keep = (_BlockReplay._keep[0], graph)
+        self.stats["captures"] += 1
+
+    def run(self, inps, outs, caches, chunk, first):
+        """the G block forwards of `chunk`; in the first pass the staged hook inputs of the group are kept"""
+        if self.graph is None:
+            self._capture(inps, caches, chunk)
+        torch.stack([inps[j] for j in chunk], out=self.sin)
+        for k, buf in self.scache.items():
+            torch.stack([caches[j][k] for j in chunk], out=buf)
+        self.graph.replay()
+        self.stats["replays"] += 1
+        for g, j in enumerate(chunk):
+            outs[j] = self.sout[g].clone()
+        if first:
+            # keep the group's hook inputs: the accumulators get every sample at the end of the pass, exactly as the eager
+            # sweep hands them over (NormBatch / HessianBatch defer their launches to one flush per block anyway)
+            c = self.filled
+            for idx, st in enumerate(self.stage):
+                if len(self.full) <= idx:
+                    self.full.append(torch.empty((self.n_groups * self.G,) + tuple(st.shape[1:]), dtype=st.dtype, device=st.device))
+                self.full[idx][c * self.G:(c + 1) * self.G].copy_(st)
+            self.filled += 1
+
+    def finish(self, wrapped):
+        """end of the first pass: the very add_batch calls of the eager hooks, in the same order, on the kept inputs"""
+        assert self.filled == self.n_groups
+        norm = {name: acc for name, acc in wrapped.items() if isinstance(acc, WrappedGPT)}
+        for s_ in range(self.n_groups * self.G if norm else 0):
+            for name, acc in norm.items():
+                acc.add_batch(self.full[self.stage_of[name]][s_], None)
+        for name, acc in wrapped.items():
+            if name not in norm:
+                # Hessians: HessianBatch concatenates the per-sample calls into one launch over [sum T, C]; the kept buffer IS
+                # that concatenation ([N, b, L, C] -> [N * b, L, C]; a [N, L, C] stack counts one sample per 2-D input)
+                full = self.full[self.stage_of[name]]
+                acc.add_batch(full.flatten(0, 1) if full.dim() == 4 else full, None)
+
+
 def wanda_prune_linear(linear, acc: WrappedGPT, sparsity, select):
     """score + select + apply for one Linear: one fused kernel call, weights zeroed in place.
     k / kth index are computed here with the reference's Python expressions (wanda_pruner.py:276, :555)."""
@@ -197,24 +363,57 @@ def sweep_blocks(pruner, model, dataloader, device, spec: SweepSpec, model_prefi
 
             return hook
 
-        handles = [subset[name].register_forward_hook(make_hook(name)) for name in wrapped]
-        try:
-            for j in my_batches:
-                with torch.no_grad():
-                    with autocast():
-                        outs[j] = _run_block(layer, inps[j], caches[j], spec)
-            if norm_batch is not None:  # one launch for the whole calibration sweep of this block
+        group = max(2, int(os.environ.get("ECF_BLOCK_GRAPH_GROUP", "16")))
+        while group > 2 and len(my_batches) % group != 0:  # the largest group size <= the setting that divides the batch count
+            group -= 1
+        replay = None
+        if not getattr(pruner, "_block_graph_failed", False) and _BlockReplay.eligible(inps, caches, my_batches, spec, group):
+            replay = _BlockReplay(layer, spec, autocast, subset, set(), group, len(my_batches) // group)
+        chunks = [my_batches[c:c + group] for c in range(0, len(my_batches), group)]
+
+        def flush():
+            if norm_batch is not None:  # one launch for the deferred hook calls
                 norm_batch.flush()
             if hess_batch is not None:
                 hess_batch.flush()
+
+        def forward_pass(first):
+            nonlocal replay
+            for ci, chunk in enumerate(chunks):
+                if replay is not None:
+                    try:
+                        replay.run(inps, outs, caches, chunk, first)
+                        continue
+                    except Exception as exc:
+                        if not (first and ci == 0 and replay.stats["replays"] == 0):
+                            raise  # outputs of earlier groups are already in place: no clean way back
+                        print(f"[ecoflap_b200] block forward not captured in a CUDA graph ({type(exc).__name__}: {exc}); running eagerly")
+                        torch.cuda.synchronize()
+                        pruner._block_graph_failed = True
+                        replay = None
+                handles = [subset[name].register_forward_hook(make_hook(name)) for name in wrapped] if first else []
+                try:
+                    for j in chunk:
+                        with torch.no_grad():
+                            with autocast():
+                                outs[j] = _run_block(layer, inps[j], caches[j], spec)
+                finally:
+                    for h in handles:
+                        h.remove()
+            if first:
+                if replay is not None:
+                    replay.finish(wrapped)
+                flush()
+
+        try:
+            forward_pass(True)
             if world > 1:  # global running means over the batches of all ranks (one all-reduce for the block)
                 if method == "wanda":
                     edist.sync_block_norms(list(wrapped.values()))
                 else:
                     edist.sync_block_hessians(list(wrapped.values()))
         finally:
-            for h in handles:
-                h.remove()
+            pass
 
         layer_items, row_items, obs_owners = [], [], []
         for name in subset:
@@ -255,14 +454,13 @@ def sweep_blocks(pruner, model, dataloader, device, spec: SweepSpec, model_prefi
         if restore is not None:
             restore()
 
-        for j in my_batches:
-            with torch.no_grad():
-                with autocast():
-                    outs[j] = _run_block(layer, inps[j], caches[j], spec)
+        forward_pass(False)
+        del replay
         inps, outs = outs, inps
 
     if stem is not None:
         stem.config.use_cache = use_cache
+    _BlockReplay._keep = None  # the graphs' memory pool goes back to the allocator
     if torch.cuda.is_available():
         torch.cuda.empty_cache()
     return model

@@ -264,6 +264,64 @@ def test_zeroth_order_prefix_cache_is_bit_identical_to_the_full_forward(monkeypa
     assert sd_c == sd_f == sd_e
 
 
+@pytest.mark.parametrize("family", ["vit", "t5"])
+def test_block_forward_graph_replay_equals_the_eager_sweep(monkeypatch, family):
+    """N2: the stage-2 block forwards replayed from one CUDA graph per block (pruners/sweep.py, _BlockReplay) against the
+    eager sweep -- bit-identical pruned weights (same kernels per sample, same norm calls in the same order)."""
+    from ecoflap_b200.compression import load_pruner
+    from ecoflap_b200.pruners.sweep import _BlockReplay
+
+    def run(flag):
+        monkeypatch.setenv("ECF_BLOCK_GRAPH", flag)
+        monkeypatch.setenv("ECF_BLOCK_GRAPH_GROUP", "2")  # 4 calibration batches = 2 groups
+        _BlockReplay.last_stats = None
+        torch.manual_seed(0)
+        if family == "vit":
+            m = cases.vit_model().cuda()
+            p = load_pruner("vit_wanda_pruner", m, cases.vit_loader(), cfg=dict(prune_spec="3-0.5-1.0-1.0", num_samples=16,
+                                                                               model_prefix="visual"))
+        else:
+            m = cases.t5_model().cuda()
+            p = load_pruner("t5_wanda_pruner", m, cases.t5_loader(), cfg=dict(prune_spec="2-0.5-1.0-1.0", num_samples=16,
+                                                                             model_prefix="t5_model"))
+        p.prune()
+        return {k: v.detach().clone() for k, v in m.state_dict().items()}, _BlockReplay.last_stats
+
+    eager, st0 = run("0")
+    replayed, st1 = run("1")
+    assert st0 is None and st1 is not None and st1["captures"] == 1 and st1["replays"] == 4, (st0, st1)
+    assert eager.keys() == replayed.keys()
+    for k in eager:
+        assert torch.equal(eager[k], replayed[k]), k
+
+
+def test_block_forward_graph_replay_sparsegpt_equals_eager(monkeypatch):
+    """SparseGPT with batch size 1 (the recipe the replay is for): 48 samples = 3 groups of 16; the Hessian launch sees the
+    same concatenated hook inputs as in the eager sweep, the second pass reads the weights OBS wrote in place."""
+    from ecoflap_b200.compression import load_pruner
+    from ecoflap_b200.pruners.sweep import _BlockReplay
+
+    def run(flag):
+        monkeypatch.setenv("ECF_BLOCK_GRAPH", flag)
+        _BlockReplay.last_stats = None
+        m = cases.vit_model().cuda()
+        p = load_pruner("vit_sparsegpt_pruner", m, cases.vit_loader(batch=1, n=48), cfg=dict(
+            prune_spec="3-0.6-1.0-1.0", num_samples=48, model_prefix="visual"))
+        p.prune()
+        return cases.prunable_state(m), _BlockReplay.last_stats
+
+    eager, _ = run("0")
+    replayed, st = run("1")
+    assert st is not None and st["captures"] == 1 and st["replays"] == 6, st  # 3 groups x 2 passes (statistics of the last block)
+    # (the Hessian kernel folds its split-T partials with floating-point atomics at this width: equal up to that order)
+    n = agree = 0
+    for k in eager:
+        n += eager[k].size
+        agree += ((eager[k] == 0) == (replayed[k] == 0)).sum()
+        np.testing.assert_allclose(replayed[k], eager[k], rtol=0, atol=2e-3 * np.abs(eager[k]).max(), err_msg=k)
+    assert agree / n >= 0.998, agree / n
+
+
 # ------------------------------------------------------------------------------------------------ UPop / LLaMA entry points
 @pytest.mark.parametrize("gran", [None, "block"])
 def test_upop_blipbert_matches_reference(gran):
