@@ -22,6 +22,7 @@ import torch
 import torch.nn as nn
 
 from .. import dist as edist
+from .. import graphs
 from .. import ops
 from ..accumulators import HessianBatch, NormBatch, SparseGPT, WrappedGPT
 
@@ -254,10 +255,14 @@ class _BlockReplay:
             # graph that uses it, so the previous block's graph is kept until this one exists.
             if _BlockReplay._keep is None:
                 _BlockReplay._keep = (torch.cuda.graph_pool_handle(), None)
-            with torch.cuda.graph(graph, pool=_BlockReplay._keep[0]), torch.no_grad(), self.autocast():
-                for g in range(G):
-                    slot["g"], slot["seen"] = g, {}
-                    self.sout[g].copy_(_run_block(self.layer, self.sin[g], self._kwargs(g), self.spec))
+
+            def body():
+                with torch.no_grad(), self.autocast():
+                    for g in range(G):
+                        slot["g"], slot["seen"] = g, {}
+                        self.sout[g].copy_(_run_block(self.layer, self.sin[g], self._kwargs(g), self.spec))
+
+            graphs.capture(graph, body, pool=_BlockReplay._keep[0], device=self.sin.device)
         finally:
             for h in handles:
                 h.remove()

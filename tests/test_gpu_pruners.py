@@ -318,7 +318,7 @@ def test_block_forward_graph_replay_sparsegpt_equals_eager(monkeypatch):
     for k in eager:
         n += eager[k].size
         agree += ((eager[k] == 0) == (replayed[k] == 0)).sum()
-        np.testing.assert_allclose(replayed[k], eager[k], rtol=0, atol=2e-3 * np.abs(eager[k]).max(), err_msg=k)
+        assert np.linalg.norm(replayed[k] - eager[k]) <= 1e-2 * np.linalg.norm(eager[k]), k  # (amplified by OBS block after block)
     assert agree / n >= 0.998, agree / n
 
 

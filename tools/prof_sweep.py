@@ -1,0 +1,13 @@
+"""cProfile of pruner.prune() on the full-size BLIP-2 (host-side hot spots of the stage-2 sweep)."""
+import cProfile, pstats, io, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import prune_wall
+which = sys.argv[1:] or ["sparsegpt"]
+pr = cProfile.Profile()
+pr.enable()
+out = prune_wall(which)
+pr.disable()
+print(out)
+s = io.StringIO()
+pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(18)
+print(s.getvalue()[:5000])
