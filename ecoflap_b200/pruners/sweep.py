@@ -466,7 +466,9 @@ def sweep_blocks(pruner, model, dataloader, device, spec: SweepSpec, model_prefi
     if stem is not None:
         stem.config.use_cache = use_cache
     _BlockReplay._keep = None  # the graphs' memory pool goes back to the allocator
-    if torch.cuda.is_available():
+    # (the reference ends _prune with torch.cuda.empty_cache(), wanda_pruner.py:289: with GBs of cached blocks that is 0.6 s of
+    # cudaFree per tower and the next tower pays the cudaMalloc again; ECF_EMPTY_CACHE=1 restores it)
+    if torch.cuda.is_available() and os.environ.get("ECF_EMPTY_CACHE", "0") == "1":
         torch.cuda.empty_cache()
     return model
 

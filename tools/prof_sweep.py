@@ -9,5 +9,8 @@ out = prune_wall(which)
 pr.disable()
 print(out)
 s = io.StringIO()
-pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(18)
-print(s.getvalue()[:5000])
+st = pstats.Stats(pr, stream=s)
+st.sort_stats("tottime").print_stats(14)
+st.print_callers("builtins.compile")
+st.sort_stats("cumtime").print_stats(30)
+print(s.getvalue()[:14000])
