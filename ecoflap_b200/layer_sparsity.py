@@ -97,6 +97,11 @@ class _ReplayedLoss:
         self._cache = {}        # id(batch) -> {boundary block index: cached output}
         self._dirty = {}        # id(batch) -> first block whose cache is not valid for the current weights
         self._own = set()       # blocks that keep their own (never refreshed) output as a structural stand-in
+        # static buffers: one set of graph variants for all batches of one shape (ECF_ZO_STATIC=0: one set per batch)
+        self.static = self.enabled and os.environ.get("ECF_ZO_STATIC", "1") != "0"
+        self._sbatch, self._scache = None, {}
+        self._static_keys = set()
+        self._cur, self._newer, self._loaded = None, set(), set()
         self.stats = {"replays": 0, "cuts_used": set(), "captures": 0}
         _ReplayedLoss.last = self  # (tests look at the statistics of the most recent run)
         if self.prefix:
@@ -174,9 +179,8 @@ class _ReplayedLoss:
         self._own = {j for ret in self._ret.values() for j, src in ret.items() if src == j} - self._boundary
 
     # -- running one variant ----------------------------------------------------------------------------------------
-    def _run(self, key, cut, dev_batch):
-        """loss_func with the blocks before `cut` answering from the cache and the boundary blocks from `cut` on writing to it"""
-        cache = self._cache.setdefault(key, {})
+    def _run(self, cache, cut, dev_batch):
+        """loss_func with the blocks before `cut` answering from `cache` and the boundary blocks from `cut` on writing to it"""
         patched, handles = [], []
         try:
             if self.prefix and self._blocks is not None:
@@ -200,6 +204,20 @@ class _ReplayedLoss:
                 del blk.forward
             for h in handles:
                 h.remove()
+
+    @staticmethod
+    def _same_struct(a, b):
+        """same nesting, tensors of the same shape / dtype, everything else equal"""
+        if torch.is_tensor(a) or torch.is_tensor(b):
+            return torch.is_tensor(a) and torch.is_tensor(b) and a.shape == b.shape and a.dtype == b.dtype and a.device == b.device
+        if isinstance(a, (list, tuple)):
+            return type(a) is type(b) and len(a) == len(b) and all(_ReplayedLoss._same_struct(x, y) for x, y in zip(a, b))
+        if isinstance(a, dict):
+            return isinstance(b, dict) and a.keys() == b.keys() and all(_ReplayedLoss._same_struct(a[k], b[k]) for k in a)
+        try:
+            return bool(a == b)
+        except Exception:
+            return False
 
     @staticmethod
     def _to_device(x, device):
@@ -234,18 +252,44 @@ class _ReplayedLoss:
                 with torch.cuda.stream(side), torch.no_grad():
                     if self.prefix and self._blocks is None:
                         self._order_blocks(dev_batch)
-                    self._run(key, 0, dev_batch)  # warm-up; fills the caches of a new batch
+                    self._run(self._cache.setdefault(key, {}), 0, dev_batch)  # warm-up; fills the caches of a new batch
                 torch.cuda.current_stream(self.device).wait_stream(side)
                 torch.cuda.synchronize(self.device)
                 self._batches[key] = (dev_batch, batch)  # (the host batch is kept alive: ids are the keys)
                 self._dirty[key] = 0
+                if self.static and self._sbatch is None:  # the first batch shapes the static buffers
+                    self._sbatch = _map_struct(dev_batch, lambda t: t.clone())
+                    self._scache = {j: _map_struct(v, lambda t: t.clone()) for j, v in self._cache[key].items()}
+                    self._cur, self._newer = key, set()
+                    self._loaded = set(self._scache)
+                if self.static and self._same_struct(self._sbatch, dev_batch) and \
+                        all(self._same_struct(self._scache.get(j), v) for j, v in self._cache[key].items()):
+                    self._static_keys.add(key)
             dev_batch = self._batches[key][0]
             cut = 0
             blk = self._block_of.get(name) if (self.prefix and self._blocks is not None) else None
             if blk is not None:
                 lim = min(blk, self._dirty[key])
                 cut = max(c for c in self._cuts if c <= lim)
-            entry = self._graphs.get((key, cut))
+            static = key in self._static_keys
+            if static:
+                # ONE set of graph variants over static batch / cache buffers serves every batch of the same shape: a
+                # capture (the suffix forward in capture mode plus the instantiation of ~1 000 nodes) costs 0.15-0.3 s,
+                # and per-batch variants made 88 of them per run.  Switching batches copies the batch in, the boundary
+                # outputs the previous batch's replays refreshed back out, and the ones this variant reads in.
+                if self._cur != key:
+                    old = self._cache[self._cur]
+                    for j in self._newer:
+                        _copy_struct(old[j], self._scache[j])
+                    _copy_struct(self._sbatch, dev_batch)
+                    self._cur, self._newer, self._loaded = key, set(), set()
+                if self.prefix and self._blocks is not None:
+                    for src in set(self._ret[cut].values()):
+                        if src not in self._loaded and src not in self._newer:
+                            _copy_struct(self._scache[src], self._cache[key][src])
+                            self._loaded.add(src)
+            gkey = ("static", cut) if static else (key, cut)
+            entry = self._graphs.get(gkey)
             if entry is None:
                 if self._pool is None:
                     self._pool = torch.cuda.graph_pool_handle()
@@ -254,9 +298,12 @@ class _ReplayedLoss:
                 # (torch's context manager, allocator flush included: measured 47.2 s against 50.1 s with the flush-free
                 # capture of graphs.py on the same box -- the other way round from the stage-2 sweep)
                 with torch.cuda.graph(graph, pool=self._pool), torch.no_grad():
-                    loss, batch_len = self._run(key, cut, dev_batch)
+                    if static:
+                        loss, batch_len = self._run(self._scache, cut, self._sbatch)
+                    else:
+                        loss, batch_len = self._run(self._cache[key], cut, dev_batch)
                 entry = (graph, loss, int(batch_len))
-                self._graphs[(key, cut)] = entry
+                self._graphs[gkey] = entry
                 self.stats["captures"] += 1
         except Exception as exc:  # not capturable: say so once, continue eagerly
             print(f"[ecoflap_b200] zeroth-order forward not captured in a CUDA graph ({type(exc).__name__}: {exc}); running eagerly")
@@ -266,6 +313,10 @@ class _ReplayedLoss:
             return self._eager(batch)
         graph, loss, batch_len = entry
         graph.replay()
+        if static and self.prefix and self._blocks is not None:  # boundary blocks this variant recomputed: newer than the batch's copy
+            upd = {j for j in self._boundary if j not in self._ret[cut]}
+            self._newer |= upd
+            self._loaded -= upd
         self.stats["replays"] += 1
         self.stats["cuts_used"].add(cut)
         # blocks in [cut, blk) were recomputed with the current weights: their caches are fresh; from blk on they are not
