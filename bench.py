@@ -278,6 +278,21 @@ def prune_wall(which=("wanda", "ecoflap"), verbose=False):
     if world > 1:  # the communicator (and its peer mappings) is set up by the first collective: not part of prune()
         dist.all_reduce(torch.zeros(1, device=dev))
         torch.cuda.synchronize()
+    # Untimed warm-up, like the W warm-up steps of the hot-path bench: one prune() of a toy BLIP-2 per registry name loads our
+    # kernels' modules (CUDA loads a kernel on its first launch), cuSOLVER / cuBLAS handles and the lazily imported Python
+    # modules -- with 8 ranks on one host that first touch once cost the first pruner of the list 18 s (N = 8, round 3).
+    with open(os.devnull, "w") as sink, contextlib.redirect_stdout(sink):
+        for reg, bs in (("blipt5_wanda_pruner", 4), ("blipt5_sparsegpt_pruner", 1)):
+            if reg == "blipt5_sparsegpt_pruner" and "sparsegpt" not in which:
+                continue
+            toy = syn.init_weights_(syn.Blip2Model(
+                vit_kw=dict(img_size=32, patch=8, dim=64, depth=2, heads=4, mlp_hidden=128),
+                t5_kw=dict(vocab=128, d_model=64, heads=4, d_kv=16, d_ff=128, depth=2), n_query=5, autocast=False), seed=5).to(dev).eval()
+            load_pruner(reg, toy, syn.text_batches(16, bs, 10, 6, 128, seed=6, with_image=32), cfg=dict(
+                t5_prune_spec="2-0.5-1.0-1.0", vit_prune_spec="2-0.5-1.0-1.0", t5_pruning_method="x", vit_pruning_method="x",
+                num_samples=16)).prune()
+            del toy
+    torch.cuda.synchronize()
     out = {}
     for name in which:
         torch.manual_seed(0)
