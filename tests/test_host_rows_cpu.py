@@ -107,3 +107,85 @@ def test_upop_quirk_is_the_default():
     from ecoflap_b200.pruners.upop import BLIPBertLayerWandaPruner
 
     assert inspect.signature(BLIPBertLayerWandaPruner.__init__).parameters["reference_uniform_quirk"].default is True
+
+
+def test_zeroth_order_prefix_cache_protocol_matches_full_forwards_on_cpu():
+    """The block-prefix cache of the zeroth-order loop (layer_sparsity._ReplayedLoss) without a GPU: the cut variants are
+    run eagerly instead of being replayed from graphs, with the same bookkeeping as __call__ (static batch / cache buffers,
+    write-back on a batch switch, dirty-from tracking), for every scored layer and three batches of the toy BLIP-2,
+    including the inexact restore that leaves a rounding residue in the weights.  Every loss must equal the full forward's."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import e2e_cases as cases
+    from ecoflap_b200.layer_sparsity import _ReplayedLoss, _copy_struct, _map_struct
+
+    torch.manual_seed(0)
+    m = cases.blip2_model().eval()
+    batches = list(cases.blip2_loader())[:3]
+
+    def loss_func(model, b, cuda):
+        return model(b)["loss"], len(b["image"])
+
+    names = [n for n, p in m.named_parameters() if n.endswith("weight") and ("blocks." in n or ".block." in n) and p.dim() == 2]
+    r = _ReplayedLoss(loss_func, m, "cpu", names)
+    r.prefix, r.static, r._stride = True, True, 2
+    r._find_blocks(names)
+    params = dict(m.named_parameters())
+    with torch.no_grad():
+        r._order_blocks(batches[0])
+        assert r._blocks is not None and len(r._blocks) == 7 and r._cuts[0] == 0 and len(r._cuts) >= 4
+        assert [type(b).__name__ for b in r._blocks] == ["EvaBlock"] * 3 + ["T5Block"] * 4  # T5Blocks, not their sub-layers
+        for b in batches:
+            k = id(b)
+            r._run(r._cache.setdefault(k, {}), 0, b)
+            r._batches[k], r._dirty[k] = (b, b), 0
+            if r._sbatch is None:
+                r._sbatch = _map_struct(b, lambda t: t.clone())
+                r._scache = {j: _map_struct(v, lambda t: t.clone()) for j, v in r._cache[k].items()}
+                r._cur, r._newer, r._loaded = k, set(), set(r._scache)
+            assert r._same_struct(r._sbatch, b)
+
+        def evaluate(b, name):
+            k, blk = id(b), r._block_of[name]
+            cut = max(c for c in r._cuts if c <= min(blk, r._dirty[k]))
+            if r._cur != k:
+                for j in r._newer:
+                    _copy_struct(r._cache[r._cur][j], r._scache[j])
+                _copy_struct(r._sbatch, b)
+                r._cur, r._newer, r._loaded = k, set(), set()
+            for src in set(r._ret[cut].values()):
+                if src not in r._loaded and src not in r._newer:
+                    _copy_struct(r._scache[src], r._cache[k][src])
+                    r._loaded.add(src)
+            loss, _ = r._run(r._scache, cut, r._sbatch)
+            upd = {j for j in r._boundary if j not in r._ret[cut]}
+            r._newer |= upd
+            r._loaded -= upd
+            r._dirty[k] = blk
+            return float(loss), cut
+
+        cuts_used = set()
+        for name in names:
+            p = params[name]
+            for b in batches:
+                z = torch.randn_like(p) * 1e-2
+                p.data.add_(z)
+                got, cut = evaluate(b, name)
+                assert got == float(loss_func(m, b, False)[0]), (name, cut)
+                p.data.sub_(2 * z)
+                got, cut = evaluate(b, name)
+                assert got == float(loss_func(m, b, False)[0]), (name, cut)
+                p.data.add_(z * 1.001)  # inexact restore
+                cuts_used.add(cut)
+        assert len(cuts_used) >= 3 and max(cuts_used) > 0  # prefixes were really skipped
+
+
+def test_block_replay_eligibility_rules():
+    """N2 (pruners/sweep.py): which calibration sweeps are replayed from a graph."""
+    from ecoflap_b200.pruners.sweep import SweepSpec, _BlockReplay
+
+    spec = SweepSpec(select="row")
+    x = [torch.zeros(1, 5, 8) for _ in range(32)]
+    caches = [{"mask": None} for _ in range(32)]
+    ok = _BlockReplay.eligible
+    assert not ok(x, caches, list(range(32)), spec, 16)  # CPU tensors: never
