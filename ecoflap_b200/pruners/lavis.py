@@ -262,6 +262,7 @@ class _BlipT5Mixin:
                 return global_sparsity_dict
             return self.get_sparsity(1 - keep_ratio, sparsity_ratio_granularity=None)
 
+        self._frozen_towers = []  # sweep.py: swept towers answer the later capture passes from their final outputs
         if self.vit_prune_spec is not None:
             self.model = self._prune(self.model, self.data_loader, device, model_prefix=self.vit_model_prefix,
                                      module_to_process=f"{self.vit_model_prefix}.blocks", n_samples=self.num_samples,
@@ -272,6 +273,7 @@ class _BlipT5Mixin:
                 self.model = self._prune(self.model, self.data_loader, device, model_prefix=self.t5_model_prefix,
                                          module_to_process=f"{self.t5_model_prefix}.{tower}.block",
                                          n_samples=self.num_samples, sparsity_ratio=sd)
+        self._frozen_towers = None
         self.model_reset(self.model, dtype_record, requires_grad_record, device)
         return self.model, global_sparsity_dict
 

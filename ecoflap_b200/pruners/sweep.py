@@ -104,6 +104,11 @@ def capture_block_inputs(pruner, model, dataloader, device, spec: SweepSpec, mod
         stem.config.use_cache = False
     layers = get_module_recursive(model, module_to_process)
     inps, caches = [], []
+    frozen = []
+    if os.environ.get("ECF_TOWER_MEMO", "1") != "0" and spec.batch_len is not None:
+        for path, f_outs, f_dim in getattr(pruner, "_frozen_towers", None) or []:
+            if path != module_to_process:
+                frozen.append((list(get_module_recursive(model, path)), f_outs, f_dim))
     layers[0] = _Catcher(layers[0], spec, inps, caches)
     try:
         seen = 0
@@ -115,10 +120,23 @@ def capture_block_inputs(pruner, model, dataloader, device, spec: SweepSpec, mod
                 if seen >= n_samples:
                     break
                 seen += spec.batch_len(batch)
+            # Towers this prune() has already swept are frozen: their last block's output for batch i is what the sweep left
+            # behind, so their blocks answer from it instead of being run again (the reference re-runs the whole pruned ViT
+            # for the T5 encoder's AND the decoder's capture pass: 2 x 128 eager ViT-g forwards in the batch-size-1 recipe).
+            patched = []
+            for f_layers, f_outs, f_dim in frozen:
+                o = f_outs[i] if i < len(f_outs) else None
+                if torch.is_tensor(o) and o.shape[f_dim] == spec.batch_len(batch):
+                    for blk in f_layers:
+                        blk.forward = (lambda *a, _o=o, **k: _o)
+                        patched.append(blk)
             try:
                 pruner._call_forward_to_cache(model, batch, device)
             except ValueError:
                 pass
+            finally:
+                for blk in patched:
+                    del blk.forward
     finally:
         layers[0] = layers[0].module
         if stem is not None:
@@ -465,6 +483,11 @@ def sweep_blocks(pruner, model, dataloader, device, spec: SweepSpec, model_prefi
 
     if stem is not None:
         stem.config.use_cache = use_cache
+    # multi-tower pruners (BLIP-2) keep the swept tower's final outputs for the capture passes of the towers that follow
+    # (capture_block_inputs): tensor-returning blocks, every batch on this rank
+    if getattr(pruner, "_frozen_towers", None) is not None and world == 1 and spec.block_output_index is None \
+            and spec.block_adapter is None and all(torch.is_tensor(t) for t in inps[:n_batches]):
+        pruner._frozen_towers.append((module_to_process, inps[:n_batches], spec.sample_dim))
     _BlockReplay._keep = None  # the graphs' memory pool goes back to the allocator
     # (the reference ends _prune with torch.cuda.empty_cache(), wanda_pruner.py:289: with GBs of cached blocks that is 0.6 s of
     # cudaFree per tower and the next tower pays the cudaMalloc again; ECF_EMPTY_CACHE=1 restores it)

@@ -322,6 +322,30 @@ def test_block_forward_graph_replay_sparsegpt_equals_eager(monkeypatch):
     assert agree / n >= 0.998, agree / n
 
 
+@pytest.mark.parametrize("reg", ["blipt5_wanda_pruner", "blipt5_sparsegpt_pruner"])
+def test_blip2_frozen_tower_memo_equals_full_capture_passes(monkeypatch, reg):
+    """The capture passes of the T5 towers answer the already-pruned ViT blocks from the outputs its sweep left behind
+    (pruners/sweep.py, ECF_TOWER_MEMO) instead of running them again: bit-identical pruned model."""
+    from ecoflap_b200.compression import load_pruner
+
+    def run(flag):
+        monkeypatch.setenv("ECF_TOWER_MEMO", flag)
+        m = cases.blip2_model().cuda()
+        bs = 1 if "sparsegpt" in reg else 4
+        p = load_pruner(reg, m, cases.blip2_loader(batch=bs), cfg=dict(
+            t5_prune_spec="2-0.5-1.0-1.0", vit_prune_spec="3-0.5-1.0-1.0", t5_pruning_method="x", vit_pruning_method="x",
+            num_samples=16))
+        p.prune()
+        return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+    full, memo = run("0"), run("1")
+    for k in full:
+        if "sparsegpt" in reg and full[k].dim() == 2:  # (the split-T Hessian kernel adds with floating-point atomics)
+            assert ((full[k] == 0) == (memo[k] == 0)).float().mean() >= 0.995, k
+        else:
+            assert torch.equal(full[k], memo[k]), k
+
+
 # ------------------------------------------------------------------------------------------------ UPop / LLaMA entry points
 @pytest.mark.parametrize("gran", [None, "block"])
 def test_upop_blipbert_matches_reference(gran):
