@@ -6,15 +6,22 @@
 //   * round 2 measured 1 709 warp instructions per 2 048-element row at 56 % issue utilisation (16 warps per SM, the
 //     loads of a row held in registers).  Here the next row is in flight as ONE bulk copy per warp that occupies no
 //     registers, the weights are re-read from shared memory in the apply pass instead of being kept (raw[] gone), and
-//     the kernel fits 3-4 CTAs per SM.
+//     the kernel runs at 64 registers: 4 CTAs = 32 warps per SM for C <= 2048.  The buffer is free after the apply pass
+//     (bracket elements are re-read from L2), so the next row's copy has the gather / ranking / patch to land.
 //   * the rows of a weight matrix have nearly the same score distribution.  A row therefore starts from the previous
-//     row's result: one counting pass at the previous threshold, then one two-pivot pass at the position the local
-//     density (elements per coarse key, carried as well) predicts for rank k -+ 16.  Almost every row is bracketed to
-//     <= ~40 elements after these three pivot evaluations; round 2 needed a 32-sample sort plus 6-7.  Whatever the
-//     guess, the bracket invariant  #(key < lo) < k <= #(key < hi)  comes from exact counts, so the carry only affects
-//     speed, never the result; a bad guess falls through to the interpolation / bisection loop of round 2.
+//     row's result: one counting pass at the previous threshold, then one at the key the local density (coarse keys per
+//     element, carried as well) predicts for rank k +- 16 on the other side of it.  Most rows are bracketed to <= 32
+//     elements after two or three pivot evaluations (4.2 on average, the seeded first rows included); round 2 needed a
+//     32-sample sort plus 6-7.  Whatever the guess, the bracket invariant  #(key < lo) < k <= #(key < hi)  comes from
+//     exact counts, so the carry only affects speed, never the result; a bad guess falls through to the interpolation /
+//     bisection loop of round 2.
+//   * the bracket is finished without atomics: a prefix sum over the lanes' candidate counts gives every candidate a
+//     slot, the lanes list the COLUMNS of their candidates, then candidate t gets its exact key from lane t; brackets
+//     that span <= 8 coarse keys rank one 32-bit word per candidate (19 key bits + 13 column bits).
 //   * a CTA owns a contiguous range of ROWS (not of 8-row batches) of the concatenated matrices of the launch, so that
 //     the warps of the grid differ by at most one row.
+//   * next to a short-row launch (row_select.cu forks a second stream) the long-row variant runs as four-warp CTAs, one per
+//     SM: both kernels then share every SM and the long rows' latency hides behind the short rows' work.
 // Requirements (host side checks them, everything else takes row_select_fast.cuh): 16-bit weights, C = NV * 256 exactly,
 // 16-byte aligned rows, no packed-mask / zero-count outputs.
 // Bound: HBM.  Algorithmic bytes per call: 2*R*C*sizeof(w) + 4*C.
