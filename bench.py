@@ -288,9 +288,10 @@ def prune_wall(which=("wanda", "ecoflap"), verbose=False):
             toy = syn.init_weights_(syn.Blip2Model(
                 vit_kw=dict(img_size=32, patch=8, dim=64, depth=2, heads=4, mlp_hidden=128),
                 t5_kw=dict(vocab=128, d_model=64, heads=4, d_kv=16, d_ff=128, depth=2), n_query=5, autocast=False), seed=5).to(dev).eval()
-            load_pruner(reg, toy, syn.text_batches(16, bs, 10, 6, 128, seed=6, with_image=32), cfg=dict(
+            n_toy = 16 * world  # (batches are sharded over the ranks: every rank gets some)
+            load_pruner(reg, toy, syn.text_batches(n_toy, bs, 10, 6, 128, seed=6, with_image=32), cfg=dict(
                 t5_prune_spec="2-0.5-1.0-1.0", vit_prune_spec="2-0.5-1.0-1.0", t5_pruning_method="x", vit_pruning_method="x",
-                num_samples=16)).prune()
+                num_samples=n_toy)).prune()
             del toy
     torch.cuda.synchronize()
     out = {}
