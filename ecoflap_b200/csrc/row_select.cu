@@ -351,8 +351,16 @@ struct RsAux {
   bool ok = false;
 };
 static RsAux* rs_aux(cudaStream_t s) {
-  static RsAux aux;
-  static bool tried = false;
+  constexpr int kMaxDev = 32;  // one second stream per device (a process may drive several)
+  static RsAux auxes[kMaxDev];
+  static bool tried_dev[kMaxDev] = {};
+  int devi = 0;
+  if (cudaGetDevice(&devi) != cudaSuccess || devi < 0 || devi >= kMaxDev) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  RsAux& aux = auxes[devi];
+  bool& tried = tried_dev[devi];
   if (!tried) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
