@@ -1,12 +1,12 @@
 """SASS evidence: per-kernel instruction histograms of the in-tree library (cuobjdump -sass), with the mnemonics that prove
 what a kernel is built on (UTCHMMA / UTCQMMA = tcgen05.mma, LDTM / STTM = tcgen05.ld/st, UTMALDG = TMA tensor load,
-LDGSTS = cp.async, HSET2 / HSETP2 = packed 16-bit compares, REDUX, ATOMS / RED) counted explicitly.
-usage: python tools/sass_histogram.py > profiles/r2/sass_histogram.txt"""
+UBLKCP = cp.async.bulk (1-D TMA copy), SYNCS = mbarrier, LDGSTS = cp.async, HSET2 / HSETP2 = packed 16-bit compares, REDUX, ATOMS / RED) counted explicitly.
+usage: python tools/sass_histogram.py > profiles/r3/sass_histogram.txt"""
 import collections, os, re, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "ecoflap_b200", "libecoflap_b200.so")
-KEY = ("UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "LDGSTS", "SYNCS", "HSET2", "HSETP2", "IDP4A", "REDUX", "ATOMS",
+KEY = ("UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "LDGSTS", "SYNCS", "HSET2", "HSETP2", "IDP4A", "REDUX", "ATOMS",
        "RED", "ATOMG", "LDG", "STG", "LDS", "STS", "SHFL", "VOTE", "BAR", "FMUL", "HFMA2", "HADD2", "LOP3", "MUFU")
 
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
