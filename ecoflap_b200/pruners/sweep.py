@@ -212,8 +212,12 @@ class _BlockReplay:
                 if torch.is_tensor(v0):
                     if not torch.is_tensor(v) or v.shape != v0.shape or v.dtype != v0.dtype or v.device != v0.device:
                         return False
-                elif v is not v0 and v != v0:
-                    return False
+                elif v is not v0:
+                    try:  # (a tuple of tensors, e.g. rotary position embeddings, has no truth value: keep the eager path)
+                        if not bool(v == v0):
+                            return False
+                    except Exception:
+                        return False
         return True
 
     def _kwargs(self, g):

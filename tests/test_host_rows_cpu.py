@@ -189,3 +189,12 @@ def test_block_replay_eligibility_rules():
     caches = [{"mask": None} for _ in range(32)]
     ok = _BlockReplay.eligible
     assert not ok(x, caches, list(range(32)), spec, 16)  # CPU tensors: never
+    if torch.cuda.is_available():
+        xg = [t.cuda() for t in x]
+        assert ok(xg, caches, list(range(32)), spec, 16)
+        assert not ok(xg, caches, list(range(16)), spec, 16)       # fewer than two groups
+        assert not ok(xg, caches, list(range(31)), spec, 16)       # the group size must divide the batch count
+        rot = [{"position_embeddings": (torch.ones(3), torch.ones(3))} for _ in range(32)]
+        assert not ok(xg, rot, list(range(32)), spec, 16)          # per-sample tuples of tensors: eager
+        shared = (torch.ones(3), torch.ones(3))
+        assert ok(xg, [{"position_embeddings": shared} for _ in range(32)], list(range(32)), spec, 16)  # one shared object
